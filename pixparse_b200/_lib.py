@@ -1,0 +1,82 @@
+"""ctypes binding of the C-ABI library (include/pixparse_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpixparse_b200.so")
+
+_lib = None
+
+EPI_STORE_BF16 = 0
+EPI_GELU_BF16 = 1
+EPI_RESID_F32 = 2
+EPI_DGELU_BF16 = 3
+EPI_REDUCE_F32 = 4
+EPI_STORE_F32 = 5
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle. Raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(
+                f"{LIB_PATH} not found: build it with `python -m pixparse_b200.build` "
+                "(there is no CPU / PyTorch fallback for the Cruller hot path)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.b200_last_error.restype = ctypes.c_char_p
+        _declare(_lib)
+    return _lib
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_longlong
+_F = ctypes.c_float
+
+# name -> argtypes; must mirror include/pixparse_b200.h exactly (tests/test_abi.py checks the symbol list)
+SIGNATURES = {
+    "b200_abi_version": [],
+    "b200_device_check": [],
+    "b200_debug_gemm_desc": [_I, _I, _I, _I, _I, _I],
+    "b200_gemm_bf16": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P],
+}
+
+
+def _declare(l):
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().b200_last_error().decode("utf-8", "replace")
+        raise B200Error(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        check(rc, name)

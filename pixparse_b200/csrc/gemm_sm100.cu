@@ -1,0 +1,474 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:   D[M,N] = sum_k A(m,k) * B(n,k)   (fp32 accumulate)
+//
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B)  ->  shared-memory ring  ->  tcgen05.mma (128 x BN x 16, cta_group::1)
+//   ->  TMEM accumulators (double buffered)   ->  tcgen05.ld  ->  fused epilogue  ->  global / TMA reduce-add
+//
+// This one kernel family replaces every library GEMM the reference's train step reaches through timm /
+// transformers (K1 patch-embed, K4 qkv, K6 proj, K7/K11 MLP, K9/K10 decoder projections, K12 LM head)
+// and their dgrad / wgrad counterparts in backward:
+//   forward  y = x W^T        : A = x  [M,K]  K-major,  B = W  [N,K]  K-major
+//   dgrad    dx = dy W        : A = dy [M,N'] K-major,  B = W  [N',K'] MN-major   (reduction dim is the row index)
+//   wgrad    dW = dy^T x      : A = dy [M',N] MN-major, B = x  [M',K] MN-major    (split-K, TMA reduce-add to fp32)
+//
+// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warps4-7 = epilogue.
+#include "common.cuh"
+#include "../../include/pixparse_b200.h"
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int EPI_COLS = 32;      // accumulator columns handled per epilogue chunk
+constexpr int EPI_BUF_BYTES = BM * EPI_COLS * 4;   // 16 KB staging tile (fp32)
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, k_blocks;
+  int splits, kb_per_split, group_m;
+  void* out;
+  long long ldo;
+  void* out2;
+  long long ldo2;
+  const float* bias;
+  const void* aux;
+  long long ld_aux;
+  // UMMA shared-memory descriptor parameters (bytes / 16-byte units), filled by the host
+  uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+};
+
+// debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
+static int g_desc_override[6] = {-1, -1, -1, -1, -1, -1};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (256 or 512 columns: powers of two)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& n_tile, int& split) {
+  const int tiles = p.m_tiles * p.n_tiles;
+  split = w / tiles;
+  const int t = w - split * tiles;
+  const int per_group = p.group_m * p.n_tiles;
+  const int group = t / per_group;
+  const int first_m = group * p.group_m;
+  const int gsize = min(p.group_m, p.m_tiles - first_m);
+  const int r = t - group * per_group;
+  m_tile = first_m + r % gsize;
+  n_tile = r / gsize;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_buf = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + 2 * EPI_BUF_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    if (EPI == B200_EPI_REDUCE_F32) prefetch_tmap(&tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int m_tile, n_tile, split;
+        decode_work(p, w, m_tile, n_tile, split);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m_tile * BM + j * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n_tile * BN + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int m_tile, n_tile, split;
+        decode_work(p, w, m_tile, n_tile, split);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t da = make_smem_desc(sa, p.a_lbo, p.a_sbo);
+          const uint64_t db = make_smem_desc(sb, p.b_lbo, p.b_sbo);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_ss(tmem_d, da + (uint64_t)(k * p.a_kadv), db + (uint64_t)(k * p.b_kadv), idesc,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (128 threads) =====================
+    const int et = threadIdx.x - 128;          // 0..127
+    const int ew = warp - 4;                   // TMEM lane quarter (== warp % 4)
+    const int row_in_tile = ew * 32 + lane;    // accumulator row owned in phase 1
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf_sel = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int m_tile, n_tile, split;
+      decode_work(p, w, m_tile, n_tile, split);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / EPI_COLS; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * EPI_COLS, r);
+        tmem_ld_wait();
+        if (c == BN / EPI_COLS - 1) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        uint8_t* buf = epi_buf + buf_sel * EPI_BUF_BYTES;
+        if (EPI == B200_EPI_REDUCE_F32) {
+          // buffer must no longer be read by the TMA reduce issued two chunks ago
+          if (et == 0) tma_wait_group_read<1>();
+          named_bar_sync(1, 128);
+        }
+        // phase 1: row-per-thread -> swizzled staging tile (conflict-free 16-byte stores)
+        {
+          uint8_t* rowp = buf + row_in_tile * 128;
+          const int sw = row_in_tile & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = v;
+          }
+        }
+        if (EPI == B200_EPI_REDUCE_F32) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            tma_reduce_add_2d(&tmap_out, buf, n_tile * BN + c * EPI_COLS, m_tile * BM);
+            tma_commit_group();
+          }
+        } else {
+          named_bar_sync(1, 128);
+          // phase 2: coalesced pass. thread -> (row = et/8 + 16*i, 4 columns at (et%8)*4)
+          const int cq = et & 7;
+          const int col = n_tile * BN + c * EPI_COLS + cq * 4;
+          float b4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) b4[e] = __ldg(p.bias + col + e);
+          }
+          const bool full4 = (col + 3 < p.N);
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int rt = (et >> 3) + 16 * i;
+            const int row = m_tile * BM + rt;
+            if (row >= p.M || col >= p.N) continue;
+            const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
+            float v[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1],
+                          __uint_as_float(raw.z) + b4[2], __uint_as_float(raw.w) + b4[3]};
+            if (EPI == B200_EPI_STORE_BF16) {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
+              if (full4) {
+                *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e]);
+              }
+            } else if (EPI == B200_EPI_GELU_BF16) {
+              // out2 = pre-activation h (bf16), out = gelu(h) computed from the rounded h (matches autocast)
+              bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
+              bf16* o2 = reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col;
+              float g[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[e] = round_bf16(v[e]);
+                g[e] = gelu_erf(v[e]);
+              }
+              if (full4) {
+                *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) {
+                    o2[e] = __float2bfloat16_rn(v[e]);
+                    o[e] = __float2bfloat16_rn(g[e]);
+                  }
+              }
+            } else if (EPI == B200_EPI_RESID_F32) {
+              // out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
+              const float* a = reinterpret_cast<const float*>(p.aux) + (long long)row * p.ld_aux + col;
+              float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
+              if (full4) {
+                const float4 rv = *reinterpret_cast<const float4*>(a);
+                *reinterpret_cast<float4*>(o) = make_float4(rv.x + v[0], rv.y + v[1], rv.z + v[2], rv.w + v[3]);
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) o[e] = a[e] + v[e];
+              }
+            } else if (EPI == B200_EPI_DGELU_BF16) {
+              // out = acc * gelu'(h), h = saved bf16 pre-activation
+              const bf16* a = reinterpret_cast<const bf16*>(p.aux) + (long long)row * p.ld_aux + col;
+              bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
+              if (full4) {
+                const uint2 hv = *reinterpret_cast<const uint2*>(a);
+                const float h0 = bf16_lo(hv.x), h1 = bf16_hi(hv.x), h2 = bf16_lo(hv.y), h3 = bf16_hi(hv.y);
+                *reinterpret_cast<uint2*>(o) =
+                    make_uint2(pack_bf16(v[0] * gelu_erf_grad(h0), v[1] * gelu_erf_grad(h1)),
+                               pack_bf16(v[2] * gelu_erf_grad(h2), v[3] * gelu_erf_grad(h3)));
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e] * gelu_erf_grad(__bfloat162float(a[e])));
+              }
+            } else if (EPI == B200_EPI_STORE_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
+              if (full4) {
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < p.N) o[e] = v[e];
+              }
+            }
+          }
+        }
+        buf_sel ^= 1;
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (EPI == B200_EPI_REDUCE_F32) {
+      if (et == 0) tma_wait_group<0>();   // all reduce-adds fully performed before exit
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
+                       int grid, cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
+    configured = true;
+  }
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, to, p);
+  B200_CHECK_LAUNCH("gemm_kernel launch");
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                        const GemmParams& p, int grid, cudaStream_t s) {
+  switch (epi) {
+    case B200_EPI_STORE_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_BF16>(ta, tb, to, p, grid, s);
+    case B200_EPI_GELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_GELU_BF16>(ta, tb, to, p, grid, s);
+    case B200_EPI_RESID_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_RESID_F32>(ta, tb, to, p, grid, s);
+    case B200_EPI_DGELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_DGELU_BF16>(ta, tb, to, p, grid, s);
+    case B200_EPI_REDUCE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_REDUCE_F32>(ta, tb, to, p, grid, s);
+    case B200_EPI_STORE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_F32>(ta, tb, to, p, grid, s);
+  }
+  set_last_error("b200_gemm_bf16: unknown epilogue %d", epi);
+  return -1;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv) {
+  g_desc_override[0] = a_lbo; g_desc_override[1] = a_sbo; g_desc_override[2] = a_kadv;
+  g_desc_override[3] = b_lbo; g_desc_override[4] = b_sbo; g_desc_override[5] = b_kadv;
+  return 0;
+}
+
+extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                              int b_mn_major, int M, int N, int K, int epilogue, void* out, long long ldo,
+                              void* out2, long long ldo2, const float* bias, const void* aux, long long ld_aux,
+                              int splits, int block_n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "b200_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  B200_CHECK_ARG(A && B && out, "b200_gemm_bf16: null operand");
+  B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "b200_gemm_bf16: lda/ldb must be multiples of 8 elements (16 B)");
+  // only the layout combinations the train step needs are instantiated
+  const int combo = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+  B200_CHECK_ARG(combo != 2, "b200_gemm_bf16: (A MN-major, B K-major) is not instantiated");
+
+  int BN = block_n;
+  if (BN == 0) BN = (N >= 192) ? 256 : 128;
+  B200_CHECK_ARG(BN == 128 || BN == 256, "b200_gemm_bf16: block_n must be 128 or 256");
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.k_blocks = (K + BK - 1) / BK;
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int sms = num_sms();
+  if (epilogue == B200_EPI_REDUCE_F32) {
+    if (splits <= 0) {
+      // fill the machine: aim for >= 2 work items per SM, but keep >= 8 k-blocks per split
+      splits = (2 * sms + tiles - 1) / tiles;
+      const int max_splits = (p.k_blocks + 7) / 8;
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+  } else {
+    splits = 1;
+  }
+  p.kb_per_split = (p.k_blocks + splits - 1) / splits;
+  p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+  p.group_m = 8;
+  p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
+  p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  // K-major: rows of 128 B, 8-row groups 1024 B apart, K advance 32 B per UMMA.
+  // MN-major: k-rows of 128 B (64 M/N elements), 8-k groups 1024 B apart (SBO), 64-element M/N chunks
+  //           BK*128 B apart (LBO), K advance 16 rows * 128 B per UMMA.
+  p.a_lbo = a_mn_major ? BK * 128 : 16; p.a_sbo = 1024; p.a_kadv = a_mn_major ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+  p.b_lbo = b_mn_major ? BK * 128 : 16; p.b_sbo = 1024; p.b_kadv = b_mn_major ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+  if (g_desc_override[0] >= 0) p.a_lbo = g_desc_override[0];
+  if (g_desc_override[1] >= 0) p.a_sbo = g_desc_override[1];
+  if (g_desc_override[2] >= 0) p.a_kadv = g_desc_override[2];
+  if (g_desc_override[3] >= 0) p.b_lbo = g_desc_override[3];
+  if (g_desc_override[4] >= 0) p.b_sbo = g_desc_override[4];
+  if (g_desc_override[5] >= 0) p.b_kadv = g_desc_override[5];
+
+  if (epilogue == B200_EPI_GELU_BF16) B200_CHECK_ARG(out2 != nullptr, "gelu epilogue needs out2 (pre-activation)");
+  if (epilogue == B200_EPI_RESID_F32 || epilogue == B200_EPI_DGELU_BF16)
+    B200_CHECK_ARG(aux != nullptr, "epilogue %d needs aux", epilogue);
+
+  CUtensorMap ta, tb, to;
+  memset(&to, 0, sizeof(to));
+  int rc;
+  {
+    // A: K-major -> global [M rows][K cols]; MN-major -> global [K rows][M cols]
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (!a_mn_major) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)M; box[0] = BK; box[1] = BM; }
+    else             { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)lda * 2;
+    rc = make_tmap(&ta, A, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
+    if (rc) return rc;
+    if (!b_mn_major) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)BN; }
+    else             { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)ldb * 2;
+    rc = make_tmap(&tb, B, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
+    if (rc) return rc;
+    if (epilogue == B200_EPI_REDUCE_F32) {
+      B200_CHECK_ARG(ldo % 4 == 0, "reduce epilogue: ldo must be a multiple of 4 floats");
+      dims[0] = (uint64_t)N; dims[1] = (uint64_t)M; box[0] = EPI_COLS; box[1] = BM;
+      strides[0] = (uint64_t)ldo * 4;
+      rc = make_tmap(&to, out, TMA_F32, 2, dims, strides, box, TMA_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+  }
+  int grid = tiles * p.splits;
+  if (grid > sms) grid = sms;
+
+  if (BN == 256) {
+    if (combo == 0) return dispatch_epi<256, false, false>(epilogue, ta, tb, to, p, grid, stream);
+    if (combo == 1) return dispatch_epi<256, false, true>(epilogue, ta, tb, to, p, grid, stream);
+    return dispatch_epi<256, true, true>(epilogue, ta, tb, to, p, grid, stream);
+  } else {
+    if (combo == 0) return dispatch_epi<128, false, false>(epilogue, ta, tb, to, p, grid, stream);
+    if (combo == 1) return dispatch_epi<128, false, true>(epilogue, ta, tb, to, p, grid, stream);
+    return dispatch_epi<128, true, true>(epilogue, ta, tb, to, p, grid, stream);
+  }
+}

@@ -1,0 +1,195 @@
+"""GPU bring-up check for the tcgen05 GEMM: every operand-layout combo, tile width, epilogue, tails, split-K.
+Writes a report to gpurun_out/gemm_check.txt. Exit code 0 only if all cases pass."""
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pixparse_b200 import ops, _lib
+
+os.makedirs("gpurun_out", exist_ok=True)
+rep = open("gpurun_out/gemm_check.txt", "w")
+def log(*a):
+    s = " ".join(str(x) for x in a)
+    print(s, flush=True); rep.write(s + "\n"); rep.flush()
+
+torch.manual_seed(0)
+dev = "cuda"
+_lib.check(_lib.lib().b200_device_check(), "device_check")
+
+def ref_mm(A, B, a_mn, b_mn):
+    a = A.float().t() if a_mn else A.float()
+    b = B.float().t() if b_mn else B.float()
+    return a @ b.t()
+
+def mk(M, N, K, a_mn, b_mn):
+    A = torch.randn((K, M) if a_mn else (M, K), device=dev).to(torch.bfloat16)
+    B = torch.randn((K, N) if b_mn else (N, K), device=dev).to(torch.bfloat16)
+    return A, B
+
+def err(out, ref):
+    d = (out.float() - ref).abs()
+    return d.max().item(), (d.norm() / (ref.norm() + 1e-12)).item()
+
+fails = 0
+def case(name, M, N, K, a_mn, b_mn, bn, tol=2e-2):
+    global fails
+    A, B = mk(M, N, K, a_mn, b_mn)
+    ref = ref_mm(A, B, a_mn, b_mn)
+    try:
+        out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epi=ops.EPI_STORE_F32, block_n=bn)
+        torch.cuda.synchronize()
+    except Exception as e:
+        log("FAIL", name, "exception", e); fails += 1; return False
+    mx, rel = err(out, ref)
+    ok = rel < 1e-5 + tol * 0 and mx < 1e-2 * (K ** 0.5)
+    ok = rel < 2e-3
+    log("PASS" if ok else "FAIL", name, f"M{M} N{N} K{K} a_mn={int(a_mn)} b_mn={int(b_mn)} bn={bn} max_abs={mx:.4g} rel={rel:.3g}")
+    if not ok:
+        fails += 1
+        torch.save({"A": A.cpu(), "B": B.cpu(), "out": out.cpu(), "ref": ref.cpu()}, f"gpurun_out/fail_{name}.pt")
+    return ok
+
+# 1. basic K-major/K-major
+ok_kk = case("kk_small", 128, 256, 64, False, False, 256)
+case("kk_small128", 128, 128, 64, False, False, 128)
+case("kk_k128", 128, 256, 128, False, False, 256)
+case("kk_multi", 512, 768, 768, False, False, 256)
+case("kk_tails", 1009, 1000, 200, False, False, 256)
+case("kk_tails128", 1009, 1000, 200, False, False, 128)
+
+# 2. K-major A, MN-major B (dgrad)
+ok_kmn = case("kmn_small", 128, 256, 64, False, True, 256)
+case("kmn_small128", 128, 128, 64, False, True, 128)
+case("kmn_multi", 512, 768, 3072, False, True, 256)
+case("kmn_tails", 1009, 1000, 200, False, True, 256)
+
+# 3. MN-major both (wgrad)
+ok_mnmn = case("mnmn_small", 128, 256, 64, True, True, 256)
+case("mnmn_small128", 128, 128, 64, True, True, 128)
+case("mnmn_multi", 768, 768, 2018, True, True, 256)
+case("mnmn_tails", 1000, 520, 1009, True, True, 256)
+
+def try_override(name, ov, a_mn, b_mn):
+    _lib.lib().b200_debug_gemm_desc(*ov)
+    r = case(name, 128, 256, 64, a_mn, b_mn, 256)
+    r2 = case(name + "_k128", 256, 512, 192, a_mn, b_mn, 256)
+    _lib.lib().b200_debug_gemm_desc(-1, -1, -1, -1, -1, -1)
+    return r and r2
+
+if not ok_kmn:
+    log("--- MN-major B failed with defaults; trying descriptor hypotheses")
+    for nm, ov in [("B_swap", (-1, -1, -1, 1024, 8192, -1)), ("B_lbo128", (-1, -1, -1, 128, 1024, -1)),
+                   ("B_sbo8192_lbo1024_kadv", (-1, -1, -1, 1024, 8192, 128))]:
+        try_override("hyp_kmn_" + nm, ov, False, True)
+if not ok_mnmn:
+    log("--- MN-major A+B failed with defaults; trying descriptor hypotheses")
+    for nm, ov in [("swap", (1024, 8192, -1, 1024, 8192, -1))]:
+        try_override("hyp_mnmn_" + nm, ov, True, True)
+
+# 4. epilogues (K-major both)
+def epi_tests():
+    global fails
+    M, N, K = 1009, 776, 320
+    A, B = mk(M, N, K, False, False)
+    bias = torch.randn(N, device=dev)
+    acc = ref_mm(A, B, False, False)
+    # STORE_BF16 + bias
+    out = ops.gemm(A, B, epi=ops.EPI_STORE_BF16, bias=bias)
+    mx, rel = err(out, acc + bias); ok = rel < 5e-3; fails += (not ok)
+    log("PASS" if ok else "FAIL", "epi_store_bf16", mx, rel)
+    # GELU
+    h = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+    g = ops.gemm(A, B, epi=ops.EPI_GELU_BF16, bias=bias, out2=h)
+    href = (acc + bias).to(torch.bfloat16)
+    gref = torch.nn.functional.gelu(href.float())
+    mx, rel = err(h, href.float()); ok = rel < 5e-3
+    mx2, rel2 = err(g, gref); ok = ok and rel2 < 8e-3; fails += (not ok)
+    log("PASS" if ok else "FAIL", "epi_gelu", mx, rel, mx2, rel2)
+    # RESID in-place
+    x = torch.randn((M, N), device=dev)
+    xref = x + acc + bias
+    ops.gemm(A, B, epi=ops.EPI_RESID_F32, bias=bias, aux=x, out=x)
+    mx, rel = err(x, xref); ok = rel < 1e-4; fails += (not ok)
+    log("PASS" if ok else "FAIL", "epi_resid_f32", mx, rel)
+    # DGELU
+    hh = torch.randn((M, N), device=dev).to(torch.bfloat16)
+    hf = hh.float().requires_grad_(True)
+    torch.nn.functional.gelu(hf).backward(acc)
+    out = ops.gemm(A, B, epi=ops.EPI_DGELU_BF16, aux=hh)
+    mx, rel = err(out, hf.grad); ok = rel < 8e-3; fails += (not ok)
+    log("PASS" if ok else "FAIL", "epi_dgelu", mx, rel)
+    # REDUCE split-K accumulate on top of existing content (MN-major both, as wgrad)
+    Mw, Nw, Kw = 776, 520, 4036
+    A2, B2 = mk(Mw, Nw, Kw, True, True)
+    base = torch.randn((Mw, Nw), device=dev)
+    ref = base + ref_mm(A2, B2, True, True)
+    for sp in (1, 4, 0):
+        o = base.clone()
+        ops.gemm(A2, B2, a_mn=True, b_mn=True, epi=ops.EPI_REDUCE_F32, out=o, splits=sp)
+        mx, rel = err(o, ref); ok = rel < 1e-4; fails += (not ok)
+        log("PASS" if ok else "FAIL", f"epi_reduce_splits{sp}", mx, rel)
+    # logits-like: padded ldo with N not multiple of 8
+    M3, N3, K3 = 300, 1003, 768
+    A3, B3 = mk(M3, N3, K3, False, False)
+    buf = torch.zeros((M3, 1008), device=dev, dtype=torch.bfloat16)
+    ops.gemm(A3, B3, epi=ops.EPI_STORE_BF16, out=buf, N=N3)
+    mx, rel = err(buf[:, :N3], ref_mm(A3, B3, False, False)); ok = rel < 5e-3 and buf[:, N3:].abs().max().item() == 0
+    fails += (not ok)
+    log("PASS" if ok else "FAIL", "epi_store_padded_ld", mx, rel)
+try:
+    epi_tests()
+except Exception as e:
+    log("FAIL epi_tests exception", repr(e)); fails += 1
+
+# 5. timing on the train-step shapes
+def bench(name, M, N, K, a_mn, b_mn, epi, bn=0, iters=20, **kw):
+    A, B = mk(M, N, K, a_mn, b_mn)
+    extra = {}
+    if epi == ops.EPI_REDUCE_F32:
+        extra["out"] = torch.zeros((M, N), device=dev)
+    elif epi == ops.EPI_RESID_F32:
+        x = torch.zeros((M, N), device=dev); extra["out"] = x; extra["aux"] = x
+    elif epi == ops.EPI_GELU_BF16:
+        extra["out2"] = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+        extra["out"] = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+    else:
+        extra["out"] = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epi=epi, block_n=bn, **extra)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epi=epi, block_n=bn, **extra)
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    tf = 2.0 * M * N * K / ms / 1e9
+    # torch reference timing
+    a = A.t() if a_mn else A
+    b = B if b_mn else B.t()
+    for _ in range(3): torch.matmul(a, b)
+    torch.cuda.synchronize(); s.record()
+    for _ in range(iters): torch.matmul(a, b)
+    e.record(); torch.cuda.synchronize()
+    ms_t = s.elapsed_time(e) / iters
+    log(f"BENCH {name}: M{M} N{N} K{K} bn={bn or 'auto'} ours {ms:.3f} ms {tf:.0f} TF/s | torch {ms_t:.3f} ms {2.0*M*N*K/ms_t/1e9:.0f} TF/s")
+
+if fails == 0 or ok_kk:
+    Mtok = 32 * 1009
+    try:
+        bench("qkv_fwd", Mtok, 2304, 768, False, False, ops.EPI_STORE_BF16)
+        bench("proj_fwd_resid", Mtok, 768, 768, False, False, ops.EPI_RESID_F32)
+        bench("fc1_fwd_gelu", Mtok, 3072, 768, False, False, ops.EPI_GELU_BF16)
+        bench("fc2_fwd_resid", Mtok, 768, 3072, False, False, ops.EPI_RESID_F32)
+        bench("fc2_fwd_resid_bn128", Mtok, 768, 3072, False, False, ops.EPI_RESID_F32, bn=128)
+        bench("lm_head", 16384, 50267, 768, False, False, ops.EPI_STORE_BF16, iters=5)
+        bench("fc1_dgrad", Mtok, 768, 3072, False, True, ops.EPI_STORE_BF16)
+        bench("fc2_dgrad", Mtok, 3072, 768, False, True, ops.EPI_STORE_BF16)
+        bench("fc1_wgrad", 3072, 768, Mtok, True, True, ops.EPI_REDUCE_F32)
+        bench("qkv_wgrad", 2304, 768, Mtok, True, True, ops.EPI_REDUCE_F32)
+        bench("proj_wgrad", 768, 768, Mtok, True, True, ops.EPI_REDUCE_F32)
+        bench("square_8192", 8192, 8192, 8192, False, False, ops.EPI_STORE_BF16, iters=10)
+    except Exception as ex:
+        log("BENCH exception", repr(ex))
+
+log("TOTAL_FAILS", fails)
+sys.exit(1 if fails else 0)
