@@ -10,7 +10,8 @@
 //   dgrad    dx = dy W        : A = dy [M,N'] K-major,  B = W  [N',K'] MN-major   (reduction dim is the row index)
 //   wgrad    dW = dy^T x      : A = dy [M',N] MN-major, B = x  [M',K] MN-major    (split-K, TMA reduce-add to fp32)
 //
-// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator, warps4-7 = epilogue.
+// Warp roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps4-7 / warps8-11 = two epilogue groups that take alternating 32-column chunks of the accumulator.
 #include "common.cuh"
 #include "../../include/pixparse_b200.h"
 
@@ -21,7 +22,7 @@ constexpr int BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int EPI_COLS = 32;      // accumulator columns handled per epilogue chunk
 constexpr int EPI_BUF_BYTES = BM * EPI_COLS * 4;   // 16 KB staging tile (fp32)
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;         // 4 control warps + 2 epilogue groups of 4 warps
 
 struct GemmParams {
   int M, N, K;
@@ -96,7 +97,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
+      mbar_init(&tmem_empty_bar[i], 256);
     }
     fence_mbar_init();
   }
@@ -189,13 +190,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (128 threads) =====================
-    const int et = threadIdx.x - 128;          // 0..127
-    const int ew = warp - 4;                   // TMEM lane quarter (== warp % 4)
+    // ===================== epilogue (2 groups x 128 threads) =====================
+    const int grp = (warp - 4) >> 2;           // chunk parity handled by this group
+    const int et = (threadIdx.x - 128) & 127;  // thread index inside the group
+    const int ew = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
     const int row_in_tile = ew * 32 + lane;    // accumulator row owned in phase 1
+    const uint32_t bar_id = 1 + grp;
+    uint8_t* buf = epi_buf + grp * EPI_BUF_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int buf_sel = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int m_tile, n_tile, split;
       decode_work(p, w, m_tile, n_tile, split);
@@ -203,21 +206,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / EPI_COLS; ++c) {
+      for (int c = grp; c < BN / EPI_COLS; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * EPI_COLS, r);
         tmem_ld_wait();
-        if (c == BN / EPI_COLS - 1) {
-          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+        if (c + 2 >= BN / EPI_COLS) {
+          // this thread's last TMEM read of the accumulator stage: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tmem_empty_bar[acc]);
         }
-        uint8_t* buf = epi_buf + buf_sel * EPI_BUF_BYTES;
+        // the staging buffer must be free: previous phase 2 done / previous TMA reduce has read it
         if (EPI == B200_EPI_REDUCE_F32) {
-          // buffer must no longer be read by the TMA reduce issued two chunks ago
-          if (et == 0) tma_wait_group_read<1>();
-          named_bar_sync(1, 128);
+          if (et == 0) tma_wait_group_read<0>();
         }
+        named_bar_sync(bar_id, 128);
         // phase 1: row-per-thread -> swizzled staging tile (conflict-free 16-byte stores)
         {
           uint8_t* rowp = buf + row_in_tile * 128;
@@ -230,16 +232,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         if (EPI == B200_EPI_REDUCE_F32) {
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (et == 0) {
             tma_reduce_add_2d(&tmap_out, buf, n_tile * BN + c * EPI_COLS, m_tile * BM);
             tma_commit_group();
           }
         } else {
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           // phase 2: coalesced pass. thread -> (row = et/8 + 16*i, 4 columns at (et%8)*4)
           const int cq = et & 7;
           const int col = n_tile * BN + c * EPI_COLS + cq * 4;
+          const int row0 = m_tile * BM + (et >> 3);
           float b4[4] = {0.f, 0.f, 0.f, 0.f};
           if (p.bias != nullptr) {
 #pragma unroll
@@ -247,79 +250,101 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               if (col + e < p.N) b4[e] = __ldg(p.bias + col + e);
           }
           const bool full4 = (col + 3 < p.N);
-#pragma unroll 2
-          for (int i = 0; i < 8; ++i) {
-            const int rt = (et >> 3) + 16 * i;
-            const int row = m_tile * BM + rt;
-            if (row >= p.M || col >= p.N) continue;
-            const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
-            float v[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1],
-                          __uint_as_float(raw.z) + b4[2], __uint_as_float(raw.w) + b4[3]};
-            if (EPI == B200_EPI_STORE_BF16) {
-              bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
-              if (full4) {
-                *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-              } else {
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e]);
-              }
-            } else if (EPI == B200_EPI_GELU_BF16) {
-              // out2 = pre-activation h (bf16), out = gelu(h) computed from the rounded h (matches autocast)
-              bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
-              bf16* o2 = reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col;
-              float g[4];
+          if (col < p.N) {
+            // batch the auxiliary loads so that 8 requests per thread are in flight
+            float4 auxf[8];
+            uint2 auxh[8];
+            if (EPI == B200_EPI_RESID_F32 && full4) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[e] = round_bf16(v[e]);
-                g[e] = gelu_erf(v[e]);
+              for (int i = 0; i < 8; ++i) {
+                const int row = row0 + 16 * i;
+                if (row < p.M)
+                  auxf[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
+                                                             (long long)row * p.ld_aux + col);
               }
-              if (full4) {
-                *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
-              } else {
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) {
-                    o2[e] = __float2bfloat16_rn(v[e]);
-                    o[e] = __float2bfloat16_rn(g[e]);
-                  }
+            }
+            if (EPI == B200_EPI_DGELU_BF16 && full4) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = row0 + 16 * i;
+                if (row < p.M)
+                  auxh[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.aux) +
+                                                            (long long)row * p.ld_aux + col);
               }
-            } else if (EPI == B200_EPI_RESID_F32) {
-              // out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
-              const float* a = reinterpret_cast<const float*>(p.aux) + (long long)row * p.ld_aux + col;
-              float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-              if (full4) {
-                const float4 rv = *reinterpret_cast<const float4*>(a);
-                *reinterpret_cast<float4*>(o) = make_float4(rv.x + v[0], rv.y + v[1], rv.z + v[2], rv.w + v[3]);
-              } else {
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) o[e] = a[e] + v[e];
-              }
-            } else if (EPI == B200_EPI_DGELU_BF16) {
-              // out = acc * gelu'(h), h = saved bf16 pre-activation
-              const bf16* a = reinterpret_cast<const bf16*>(p.aux) + (long long)row * p.ld_aux + col;
-              bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
-              if (full4) {
-                const uint2 hv = *reinterpret_cast<const uint2*>(a);
-                const float h0 = bf16_lo(hv.x), h1 = bf16_hi(hv.x), h2 = bf16_lo(hv.y), h3 = bf16_hi(hv.y);
-                *reinterpret_cast<uint2*>(o) =
-                    make_uint2(pack_bf16(v[0] * gelu_erf_grad(h0), v[1] * gelu_erf_grad(h1)),
-                               pack_bf16(v[2] * gelu_erf_grad(h2), v[3] * gelu_erf_grad(h3)));
-              } else {
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e] * gelu_erf_grad(__bfloat162float(a[e])));
-              }
-            } else if (EPI == B200_EPI_STORE_F32) {
-              float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-              if (full4) {
-                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              } else {
-                for (int e = 0; e < 4; ++e)
-                  if (col + e < p.N) o[e] = v[e];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rt = (et >> 3) + 16 * i;
+              const int row = row0 + 16 * i;
+              if (row >= p.M) continue;
+              const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
+              float v[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1],
+                            __uint_as_float(raw.z) + b4[2], __uint_as_float(raw.w) + b4[3]};
+              if (EPI == B200_EPI_STORE_BF16) {
+                bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
+                if (full4) {
+                  *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e]);
+                }
+              } else if (EPI == B200_EPI_GELU_BF16) {
+                // out2 = pre-activation h (bf16), out = gelu(h) computed from the rounded h (matches autocast)
+                bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
+                bf16* o2 = reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col;
+                float g[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[e] = round_bf16(v[e]);
+                  g[e] = gelu_erf(v[e]);
+                }
+                if (full4) {
+                  *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                  *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (col + e < p.N) {
+                      o2[e] = __float2bfloat16_rn(v[e]);
+                      o[e] = __float2bfloat16_rn(g[e]);
+                    }
+                }
+              } else if (EPI == B200_EPI_RESID_F32) {
+                // out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
+                float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
+                if (full4) {
+                  const float4 rv = auxf[i];
+                  *reinterpret_cast<float4*>(o) = make_float4(rv.x + v[0], rv.y + v[1], rv.z + v[2], rv.w + v[3]);
+                } else {
+                  const float* a = reinterpret_cast<const float*>(p.aux) + (long long)row * p.ld_aux + col;
+                  for (int e = 0; e < 4; ++e)
+                    if (col + e < p.N) o[e] = a[e] + v[e];
+                }
+              } else if (EPI == B200_EPI_DGELU_BF16) {
+                // out = acc * gelu'(h), h = saved bf16 pre-activation
+                bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
+                if (full4) {
+                  const uint2 hv = auxh[i];
+                  const float h0 = bf16_lo(hv.x), h1 = bf16_hi(hv.x), h2 = bf16_lo(hv.y), h3 = bf16_hi(hv.y);
+                  *reinterpret_cast<uint2*>(o) =
+                      make_uint2(pack_bf16(v[0] * gelu_erf_grad(h0), v[1] * gelu_erf_grad(h1)),
+                                 pack_bf16(v[2] * gelu_erf_grad(h2), v[3] * gelu_erf_grad(h3)));
+                } else {
+                  const bf16* a = reinterpret_cast<const bf16*>(p.aux) + (long long)row * p.ld_aux + col;
+                  for (int e = 0; e < 4; ++e)
+                    if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e] * gelu_erf_grad(__bfloat162float(a[e])));
+                }
+              } else if (EPI == B200_EPI_STORE_F32) {
+                float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
+                if (full4) {
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                  for (int e = 0; e < 4; ++e)
+                    if (col + e < p.N) o[e] = v[e];
+                }
               }
             }
           }
         }
-        buf_sel ^= 1;
       }
       if (++acc == 2) {
         acc = 0;
@@ -391,6 +416,16 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
   const int combo = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
   B200_CHECK_ARG(combo != 2, "b200_gemm_bf16: (A MN-major, B K-major) is not instantiated");
 
+  if (epilogue == B200_EPI_STORE_BF16 || epilogue == B200_EPI_GELU_BF16 || epilogue == B200_EPI_DGELU_BF16)
+    B200_CHECK_ARG(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+                   "b200_gemm_bf16: bf16 output needs ldo %% 4 == 0 and 8-byte alignment (ldo=%lld)", ldo);
+  if (epilogue == B200_EPI_GELU_BF16)
+    B200_CHECK_ARG(ldo2 % 4 == 0, "b200_gemm_bf16: out2 needs ldo2 %% 4 == 0");
+  if (epilogue == B200_EPI_RESID_F32 || epilogue == B200_EPI_STORE_F32)
+    B200_CHECK_ARG(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                   "b200_gemm_bf16: fp32 output needs ldo %% 4 == 0 and 16-byte alignment");
+  if (epilogue == B200_EPI_RESID_F32 || epilogue == B200_EPI_DGELU_BF16)
+    B200_CHECK_ARG(ld_aux % 4 == 0, "b200_gemm_bf16: aux needs ld_aux %% 4 == 0");
   int BN = block_n;
   if (BN == 0) BN = (N >= 192) ? 256 : 128;
   B200_CHECK_ARG(BN == 128 || BN == 256, "b200_gemm_bf16: block_n must be 128 or 256");

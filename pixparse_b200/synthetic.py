@@ -1,0 +1,57 @@
+"""Synthetic workload generator for the Cruller train step (BASELINE.json configs).
+
+Pure CPU torch; shared by the benchmark, the tests and the oracle so that every arm sees byte-identical
+inputs for a given seed. Mirrors what the reference's data pipeline hands to ``train_step``
+(/root/reference/src/pixparse/task/task_cruller_pretrain.py:236-242, data/preprocess.py:62-68,97-101):
+
+    image  (B, 1, H, W) float32, already normalised with mean 0.5 / std 0.5
+    text   (B, Lt) int64   = [<s_pretrain>, tok..., </s>, <pad>...]
+    target (B, Lt) int64   = text with PAD -> -100 and the prompt token -> -100
+"""
+import torch
+
+PAD_ID = 1
+EOS_ID = 2
+BART_VOCAB = 50265
+# tokens are added to the tokenizer in sorted() order: '<s_pretrain>' < '<sep/>'
+# (task_cruller_pretrain.py:92-99) -> ids 50265 and 50266, vocab 50267
+S_PRETRAIN_ID = 50265
+SEP_ID = 50266
+PRETRAIN_VOCAB = 50267
+
+
+def synthetic_pages_u8(batch, height=1100, width=850, seed=0):
+    """uint8 'L' pages: white background with random dark rectangles ("text lines")."""
+    g = torch.Generator().manual_seed(seed)
+    pages = torch.full((batch, height, width), 255, dtype=torch.uint8)
+    for b in range(batch):
+        n = int(torch.randint(20, 60, (1,), generator=g))
+        ys = torch.randint(0, height - 12, (n,), generator=g)
+        xs = torch.randint(0, width - 40, (n,), generator=g)
+        hs = torch.randint(4, 12, (n,), generator=g)
+        ws = torch.randint(20, width // 2, (n,), generator=g)
+        vs = torch.randint(0, 96, (n,), generator=g)
+        for y, x, h, w, v in zip(ys.tolist(), xs.tolist(), hs.tolist(), ws.tolist(), vs.tolist()):
+            pages[b, y:y + h, x:min(width, x + w)] = v
+    return pages
+
+
+def synthetic_batch(batch, image_size=(576, 448), text_len=513, vocab=PRETRAIN_VOCAB, seed=0,
+                    min_eos_frac=0.75, start_id=S_PRETRAIN_ID):
+    """Return (image, text, target) exactly in the layout the reference's train_step consumes."""
+    g = torch.Generator().manual_seed(seed)
+    H, W = image_size
+    image = torch.rand((batch, 1, H, W), generator=g, dtype=torch.float32)
+    image = (image - 0.5) / 0.5
+    text = torch.randint(3, min(vocab, BART_VOCAB), (batch, text_len), generator=g, dtype=torch.int64)
+    text[:, 0] = start_id
+    lo = max(2, int(min_eos_frac * text_len))
+    eos_pos = torch.randint(lo, text_len, (batch,), generator=g)
+    for b in range(batch):
+        p = int(eos_pos[b])
+        text[b, p] = EOS_ID
+        text[b, p + 1:] = PAD_ID
+    target = text.clone()
+    target[text == PAD_ID] = -100
+    target[:, 0] = -100   # prompt_end_token == task_start_token at position 0 (data/preprocess.py:97-101)
+    return image, text, target
