@@ -48,6 +48,76 @@ int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, 
                    int M, int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
                    const float* bias, const void* aux, long long ld_aux, int splits, int block_n, void* stream);
 
+/* ---- attention (tcgen05, flash-style, head_dim 64) ---------------------------------------------
+ * q/k/v are [B, S, row] bf16 activations with `ld*` elements between tokens; head h occupies columns
+ * [*_col0 + 64 h, *_col0 + 64 h + 64). out is [B, Sq, ld_out] (head h at column 64 h); lse is [B, H, Sq] fp32.
+ * Replaces F.scaled_dot_product_attention in timm Attention (encoder, non-causal) and BartAttention
+ * (decoder causal self-attention and cross-attention; modeling_bart.py:185-258).
+ */
+int b200_attention_fwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                       const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
+                       int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
+
+/* backward: dq/dk/dv (bf16, strided like q/k/v) from d_o; `o` and `lse` are the forward outputs.
+ * workspace: b200_attention_bwd_workspace_bytes(B, H, Sq) bytes of device memory (fp32 dQ accumulator + row sums). */
+long long b200_attention_bwd_workspace_bytes(int B, int H, int Sq);
+int b200_attention_bwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                       const void* v, long long ldv, int v_col0, const void* o, long long ld_o, const void* d_o,
+                       long long ld_do, int do_col0, const float* lse, void* dq, long long ld_dq, int dq_col0,
+                       void* dk, long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
+                       void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
+                       void* stream);
+
+/* ---- LayerNorm (timm Block.norm1/norm2/norm; BART layernorm_embedding / *_layer_norm) --------------
+ * fwd: y = (x - mean) * rstd * gamma + beta; x fp32 [rows, dim]; optional bf16 and/or fp32 outputs; mean/rstd saved.
+ * bwd: dy = dy_bf16 + dy_f32 (either may be NULL); dx = LNbwd(dy) + dres_f32 (optional residual-path gradient);
+ *      dgamma/dbeta are accumulated (+=).
+ */
+int b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                       float* mean, float* rstd, int rows, int dim, float eps, void* stream);
+int b200_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
+                       const float* mean, const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16,
+                       float* dgamma, float* dbeta, int rows, int dim, void* stream);
+
+/* ---- HBM-bound helpers ---------------------------------------------------------------------------- */
+/* out[n] += sum_m dy[m, n]  (bias gradients of every nn.Linear) */
+int b200_colsum_bf16(const void* dy, long long ld, int rows, int cols, float* out, void* stream);
+/* timm PatchEmbed: unfold (B, C, H, W) fp32 pixels into [B*gh*gw, C*P*P] bf16 rows for the patch GEMM */
+int b200_patch_unfold(const float* image, void* patches_bf16, int B, int C, int H, int W, int P,
+                      long long ld_patches, void* stream);
+/* timm _pos_embed: x[b,0] = cls + pos[0]; x[b,1+p] = proj[b,p] + pos[1+p]; and its backward */
+int b200_tokens_assemble(const void* proj_bf16, const float* cls, const float* pos, float* x, int B, int S, int D,
+                         void* stream);
+int b200_tokens_assemble_bwd(const float* dx, void* dproj_bf16, float* dcls, float* dpos, int B, int S, int D,
+                             void* stream);
+/* BartDecoder embedding: x[b,t] = embed_tokens[ids[b,t]] * scale + embed_positions[t + pos_offset]; and backward
+ * (scatter-add, skipping padding_idx like nn.Embedding(padding_idx)) */
+int b200_embed_fwd(const long long* ids, const float* tok_emb, const float* pos_emb, float* x, int B, int T, int D,
+                   int pos_offset, float scale, void* stream);
+int b200_embed_bwd(const long long* ids, const float* dx, float* d_tok_emb, float* d_pos_emb, int B, int T, int D,
+                   int pos_offset, float scale, long long padding_idx, void* stream);
+int b200_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+
+/* ---- loss + optimizer ------------------------------------------------------------------------------
+ * nn.CrossEntropyLoss(ignore_index) fwd+bwd in one pass (task_cruller_pretrain.py:118,251-254):
+ *   ce_prepare: stats[0] = #valid targets, stats[1] = 0
+ *   ce_fwd_bwd: stats[1] += mean loss; dlogits = (softmax - onehot) * grad_scale / #valid (may alias logits)
+ * grad_norm: deterministic global L2 norm of the flat gradient arena; out3 = {sumsq, norm, clip coefficient}
+ *   (timm dispatch_clip_grad 'norm' -> clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)))
+ * adamw_step: torch.optim.AdamW semantics over the flat arena, per-tensor lr_scale / weight_decay segments
+ *   {int64 end; float lr_scale; float weight_decay}; also refreshes the bf16 shadow weights and zeroes grads.
+ */
+int b200_ce_prepare(const long long* targets, int n, long long ignore_index, float* stats, void* stream);
+int b200_ce_fwd_bwd(const void* logits_bf16, long long ld, const long long* targets, void* dlogits_bf16,
+                    long long ldd, float* row_loss, float* stats, int rows, int vocab, long long ignore_index,
+                    float grad_scale, void* stream);
+int b200_grad_norm(const float* grads, long long n, float* workspace, float* out3, float max_norm, float pre_scale,
+                   void* stream);
+int b200_grad_norm_workspace_floats(void);
+int b200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, long long n,
+                    const void* segments, int num_segments, const float* norm_stats, float grad_scale, float lr,
+                    float beta1, float beta2, float eps, int step, int zero_grad, void* stream);
+
 /* bring-up aid: override the UMMA shared-memory descriptor fields (-1 keeps the default) */
 int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv);
 

@@ -48,6 +48,23 @@ SIGNATURES = {
     "b200_abi_version": [],
     "b200_device_check": [],
     "b200_debug_gemm_desc": [_I, _I, _I, _I, _I, _I],
+    "b200_attention_fwd": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "b200_attention_bwd": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _L, _I, _P, _P, _L, _I, _P, _L, _I, _P, _L,
+                           _I, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "b200_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "b200_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "b200_colsum_bf16": [_P, _L, _I, _I, _P, _P],
+    "b200_patch_unfold": [_P, _P, _I, _I, _I, _I, _I, _L, _P],
+    "b200_tokens_assemble": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "b200_tokens_assemble_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "b200_embed_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "b200_embed_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _L, _P],
+    "b200_cast_f32_bf16": [_P, _P, _L, _P],
+    "b200_ce_prepare": [_P, _I, _L, _P, _P],
+    "b200_ce_fwd_bwd": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _L, _F, _P],
+    "b200_grad_norm": [_P, _L, _P, _P, _F, _F, _P],
+    "b200_grad_norm_workspace_floats": [],
+    "b200_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _I, _P, _F, _F, _F, _F, _F, _I, _I, _P],
     "b200_gemm_bf16": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P],
 }
 
@@ -57,6 +74,8 @@ def _declare(l):
         fn = getattr(l, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    l.b200_attention_bwd_workspace_bytes.argtypes = [_I, _I, _I]
+    l.b200_attention_bwd_workspace_bytes.restype = ctypes.c_longlong
 
 
 def check(rc, what):

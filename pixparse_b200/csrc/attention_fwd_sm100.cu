@@ -1,0 +1,304 @@
+// Flash-style attention forward for sm_100a, head_dim 64, bf16 in / bf16 out, fp32 softmax statistics.
+//
+//   S = Q K^T        tcgen05.mma  (A = Q tile, B = K tile, both K-major in shared memory via TMA)  -> TMEM
+//   P = softmax(S)   one thread per query row: tcgen05.ld, online max/sum in registers, exp2, bf16 pack,
+//                    tcgen05.st back into TMEM (P never touches shared memory)
+//   O += P V         tcgen05.mma  (A = P from TMEM, B = V tile MN-major in shared memory)         -> TMEM
+//
+// One CTA per (128-query tile, head, batch); two CTAs are co-resident per SM (80 KB smem, 256 TMEM columns each)
+// so the MMA phases of one overlap the softmax phase of the other.
+//
+// Serves the three attention shapes of the Cruller step:
+//   encoder self-attention (non-causal, Sq = Sk = 1009 / 2509), decoder causal self-attention (Sq = Sk = T),
+//   decoder cross-attention over image tokens (Sq = T, Sk = S, no mask).
+// Replaces torch SDPA reached from timm Attention (fused_attn) and BartAttention (sdpa).
+#include "common.cuh"
+#include "../../include/pixparse_b200.h"
+
+namespace b200 {
+
+constexpr int ATT_BM = 128;   // queries per CTA
+constexpr int ATT_BN = 128;   // keys per inner tile
+constexpr int ATT_D = 64;     // head dim
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;   // 16 KB
+constexpr int ATT_SMEM = ATT_TILE_BYTES * 5 + 256 + 1024;
+
+constexpr uint32_t TM_S = 0;      // 128 columns: S (fp32)
+constexpr uint32_t TM_P = 128;    // 64 columns:  P (bf16 pairs)
+constexpr uint32_t TM_O = 192;    // 64 columns:  O (fp32)
+
+struct AttFwdParams {
+  int B, H, Sq, Sk;
+  int causal;
+  float scale_log2;        // softmax scale * log2(e)
+  bf16* out;               // [B, Sq, ld_out] bf16, head h at column h*64
+  long long ld_out;
+  float* lse;              // [B, H, Sq] natural-log logsumexp of the scaled scores
+  int q_col0, k_col0, v_col0;   // column offsets of head 0 inside the Q / K / V row
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;          // 2 stages
+  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;      // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* v_full = bars + 3;     // [2]
+  uint64_t* kv_empty = bars + 5;   // [2]
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_full = bars + 8;
+  uint64_t* o_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = gridDim.x - 1 - blockIdx.x;   // heavy (late, causal) tiles first
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int q0 = q_tile * ATT_BM;
+
+  int n_tiles = (p.Sk + ATT_BN - 1) / ATT_BN;
+  if (p.causal) {
+    const int last_key = q0 + ATT_BM - 1 + (p.Sk - p.Sq);   // largest key index any row of this tile may see
+    const int lim = last_key / ATT_BN + 1;
+    if (lim < n_tiles) n_tiles = lim;
+  }
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+  }
+  if (warp == 5 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc<256>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tmap_q, q_full, p.q_col0 + h * ATT_D, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sK + s * ATT_TILE_BYTES, &tmap_k, &k_full[s], p.k_col0 + h * ATT_D, j * ATT_BN, b);
+        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sV + s * ATT_TILE_BYTES, &tmap_v, &v_full[s], p.v_col0 + h * ATT_D, j * ATT_BN, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, false, false);   // S = Q K^T
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, false, true);     // O = P V (V is MN-major)
+      mbar_wait(q_full, 0);
+      const uint64_t dq = make_smem_desc(smem_u32(sQ), 16, 1024);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[s], ph);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc(smem_u32(sK + s * ATT_TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_ss(tmem_base + TM_S, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        // P_j ready (and O rescaled) -> O += P V
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        const uint64_t dv = make_smem_desc(smem_u32(sV + s * ATT_TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          umma_ts(tmem_base + TM_O, tmem_base + TM_P + 8 * k, dv + (uint64_t)(128 * k), idesc_o,
+                  (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[s]);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / output (128 threads, one query row each) =====================
+    const int row = warp * 32 + lane;
+    const int qidx = q0 + row;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int causal_shift = p.Sk - p.Sq;
+    float m_run = -INFINITY;   // running max in the scaled log2 domain
+    float l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int k0 = j * ATT_BN;
+      const bool need_mask = (k0 + ATT_BN > p.Sk) || (p.causal && (k0 + ATT_BN - 1 > q0 + causal_shift));
+      int kmax = p.Sk - 1;                                   // largest visible key index for this row
+      if (p.causal) kmax = min(kmax, qidx + causal_shift);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < ATT_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + TM_S + c * 32, r);
+        tmem_ld_wait();
+        if (need_mask) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (k0 + c * 32 + e <= kmax) mx = fmaxf(mx, __uint_as_float(r[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // fully masked so far: keep exp2 finite
+      const float alpha = exp2f(m_run - m_use);                  // 0 on the first tile (m_run = -inf)
+      // ---- rescale the running O (TMEM) once the previous P V has retired
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+          for (int c = 0; c < ATT_D / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(lane_addr + TM_O + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              lo[e] = r[e];
+              hi[e] = r[16 + e];
+            }
+            tmem_st_32x16(lane_addr + TM_O + c * 32, lo);
+            tmem_st_32x16(lane_addr + TM_O + c * 32 + 16, hi);
+          }
+        }
+      }
+      // ---- pass 2: P = exp2(S * scale - m), row sum, bf16 pack -> TMEM
+      float l_tile = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < ATT_BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(lane_addr + TM_S + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float p0 = exp2f(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_use));
+          float p1 = exp2f(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_use));
+          if (need_mask) {
+            if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
+            if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
+          }
+          l_tile += p0 + p1;
+          pk[e] = pack_bf16(p0, p1);
+        }
+        tmem_st_32x16(lane_addr + TM_P + c * 16, pk);
+      }
+      tmem_st_wait();
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16, logsumexp
+    mbar_wait(o_full, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    // tcgen05.ld is warp-collective: every lane issues the loads, only the stores are predicated
+    const bool row_ok = qidx < p.Sq;
+    bf16* orow = p.out + ((long long)b * p.Sq + (row_ok ? qidx : 0)) * p.ld_out + h * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < ATT_D / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(lane_addr + TM_O + c * 32, r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[8 * v4 + 0]) * inv_l, __uint_as_float(r[8 * v4 + 1]) * inv_l);
+          o.y = pack_bf16(__uint_as_float(r[8 * v4 + 2]) * inv_l, __uint_as_float(r[8 * v4 + 3]) * inv_l);
+          o.z = pack_bf16(__uint_as_float(r[8 * v4 + 4]) * inv_l, __uint_as_float(r[8 * v4 + 5]) * inv_l);
+          o.w = pack_bf16(__uint_as_float(r[8 * v4 + 6]) * inv_l, __uint_as_float(r[8 * v4 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) = o;
+        }
+      }
+    }
+    if (row_ok && p.lse)
+      p.lse[((long long)b * p.H + h) * p.Sq + qidx] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<256>(tmem_base);
+}
+
+// 3-D tensor map over a [B, S, width] bf16 activation whose rows are `ld` elements apart; box = 64 x 128 x 1
+int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld) {
+  uint64_t dims[3] = {(uint64_t)width, (uint64_t)S, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)S};
+  uint32_t box[3] = {64, 128, 1};
+  return make_tmap(m, base, TMA_BF16, 3, dims, strides, box, TMA_SWIZZLE_128B);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_attention_fwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                                  const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
+                                  int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  B200_CHECK_ARG(head_dim == ATT_D, "b200_attention_fwd: head_dim %d unsupported (only 64)", head_dim);
+  B200_CHECK_ARG(q && k && v && out && B > 0 && H > 0 && Sq > 0 && Sk > 0, "b200_attention_fwd: bad arguments");
+  B200_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ld_out % 8 == 0,
+                 "b200_attention_fwd: row strides must be multiples of 8 elements");
+  B200_CHECK_ARG(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "b200_attention_fwd: column offsets % 8");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "b200_attention_fwd: out must be 16-byte aligned");
+  if (causal) B200_CHECK_ARG(Sk >= Sq, "b200_attention_fwd: causal attention needs Sk >= Sq");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)H * ATT_D, ldq))) return rc;
+  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)H * ATT_D, ldk))) return rc;
+  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)H * ATT_D, ldv))) return rc;
+  AttFwdParams p;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out; p.lse = lse;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attention_fwd)");
+    configured = true;
+  }
+  dim3 grid((Sq + ATT_BM - 1) / ATT_BM, H, B);
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
+  B200_CHECK_LAUNCH("attention_fwd");
+  return 0;
+}

@@ -1,0 +1,275 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C-ABI, against plain PyTorch fp32
+references of the same op (tolerances written per test)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+# ------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (1009, 1000, 200, 256), (515, 776, 1032, 128)])
+def test_gemm_layouts(cuda_lib, a_mn, b_mn, M, N, K, bn):
+    from pixparse_b200 import ops
+    torch.manual_seed(1)
+    pad8 = lambda n: (n + 7) // 8 * 8
+    # MN-major operands keep M / N contiguous: the row stride must be a multiple of 8 elements
+    A = torch.randn((K, pad8(M)) if a_mn else (M, K), device=DEV).bfloat16()
+    B = torch.randn((K, pad8(N)) if b_mn else (N, K), device=DEV).bfloat16()
+    Af = A.float()[:, :M].t() if a_mn else A.float()
+    Bf = B.float()[:, :N] if b_mn else B.float().t()
+    ref = Af @ Bf
+    out = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, epi=ops.EPI_STORE_F32, block_n=bn, M=M, N=N, K=K)
+    assert rel_err(out, ref) < 1e-5      # bf16 products are exact in fp32; only accumulation order differs
+
+
+def test_gemm_epilogues(cuda_lib):
+    from pixparse_b200 import ops
+    torch.manual_seed(2)
+    M, N, K = 1009, 776, 320
+    A = torch.randn((M, K), device=DEV).bfloat16()
+    B = torch.randn((N, K), device=DEV).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    acc = A.float() @ B.float().t()
+    out = ops.gemm(A, B, epi=ops.EPI_STORE_BF16, bias=bias)
+    assert rel_err(out, acc + bias) < 4e-3            # one bf16 rounding of the output
+    h = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    g = ops.gemm(A, B, epi=ops.EPI_GELU_BF16, bias=bias, out2=h)
+    href = (acc + bias).bfloat16()
+    assert rel_err(h, href) < 1e-3
+    assert rel_err(g, F.gelu(href.float())) < 4e-3
+    x = torch.randn((M, N), device=DEV)
+    xref = x + acc + bias
+    ops.gemm(A, B, epi=ops.EPI_RESID_F32, bias=bias, aux=x, out=x)
+    assert rel_err(x, xref) < 1e-5
+    hh = torch.randn((M, N), device=DEV).bfloat16()
+    hf = hh.float().requires_grad_(True)
+    F.gelu(hf).backward(acc)
+    out = ops.gemm(A, B, epi=ops.EPI_DGELU_BF16, aux=hh)
+    assert rel_err(out, hf.grad) < 4e-3
+
+
+def test_gemm_splitk_reduce_accumulates(cuda_lib):
+    from pixparse_b200 import ops
+    torch.manual_seed(3)
+    Mw, Nw, Kw = 776, 520, 4036
+    A = torch.randn((Kw, Mw), device=DEV).bfloat16()
+    B = torch.randn((Kw, Nw), device=DEV).bfloat16()
+    base = torch.randn((Mw, Nw), device=DEV)
+    ref = base + A.float().t() @ B.float()
+    for sp in (1, 4, 0):
+        o = base.clone()
+        ops.gemm(A, B, a_mn=True, b_mn=True, epi=ops.EPI_REDUCE_F32, out=o, splits=sp)
+        assert rel_err(o, ref) < 1e-5
+
+
+def test_gemm_rejects_bad_alignment(cuda_lib):
+    from pixparse_b200 import ops, _lib
+    A = torch.randn((128, 64), device=DEV).bfloat16()
+    B = torch.randn((130, 64), device=DEV).bfloat16()
+    out = torch.empty((128, 130), device=DEV, dtype=torch.bfloat16)   # ldo = 130: not a multiple of 4
+    with pytest.raises(_lib.B200Error):
+        ops.gemm(A, B, out=out)
+
+
+# ------------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, causal, scale):
+    # q: [B,H,Sq,64] float
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        Sq, Sk = s.shape[-2:]
+        mask = torch.ones(Sq, Sk, device=s.device, dtype=torch.bool).tril(Sk - Sq)
+        s = s.masked_fill(~mask, float("-inf"))
+    p = s.softmax(-1)
+    return p @ v, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,causal", [
+    (2, 2, 128, 128, False), (1, 3, 1009, 1009, False), (2, 2, 512, 512, True), (2, 2, 200, 1009, False),
+    (1, 2, 4, 300, False), (1, 2, 4, 4, True), (1, 1, 77, 77, True)])
+def test_attention_fwd(cuda_lib, B, H, Sq, Sk, causal):
+    from pixparse_b200 import ops
+    torch.manual_seed(4)
+    D = H * 64
+    # packed projections like the model produces them: q from one tensor, k|v from another
+    qbuf = torch.randn((B * Sq, D), device=DEV).bfloat16()
+    kvbuf = torch.randn((B * Sk, 2 * D), device=DEV).bfloat16()
+    out, lse = ops.attention_fwd(qbuf, kvbuf, kvbuf, B=B, H=H, Sq=Sq, Sk=Sk, k_col0=0, v_col0=D, causal=causal)
+    q = qbuf.float().view(B, Sq, H, 64).transpose(1, 2)
+    k = kvbuf[:, :D].float().reshape(B, Sk, H, 64).transpose(1, 2)
+    v = kvbuf[:, D:].float().reshape(B, Sk, H, 64).transpose(1, 2)
+    oref, lref = _attn_ref(q, k, v, causal, 0.125)
+    o = out.float().view(B, Sq, H, 64).transpose(1, 2)
+    assert rel_err(o, oref) < 1e-2           # P and O are rounded to bf16
+    assert (lse - lref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,causal", [
+    (2, 2, 128, 128, False), (1, 3, 1009, 1009, False), (2, 2, 512, 512, True), (2, 2, 200, 1009, False),
+    (1, 2, 4, 300, False), (1, 2, 4, 4, True), (1, 1, 300, 300, True)])
+def test_attention_bwd(cuda_lib, B, H, Sq, Sk, causal):
+    from pixparse_b200 import ops
+    torch.manual_seed(11)
+    D = H * 64
+    qbuf = torch.randn((B * Sq, D), device=DEV).bfloat16()
+    kvbuf = torch.randn((B * Sk, 2 * D), device=DEV).bfloat16()
+    dout = torch.randn((B * Sq, D), device=DEV).bfloat16()
+    out, lse = ops.attention_fwd(qbuf, kvbuf, kvbuf, B=B, H=H, Sq=Sq, Sk=Sk, k_col0=0, v_col0=D, causal=causal)
+    dq = torch.full((B * Sq, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    dkv = torch.full((B * Sk, 2 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention_bwd(qbuf, kvbuf, kvbuf, out, dout, lse, dq, dkv, dkv, B=B, H=H, Sq=Sq, Sk=Sk, k_col0=0, v_col0=D,
+                      dk_col0=0, dv_col0=D, causal=causal)
+    q = qbuf.float().view(B, Sq, H, 64).transpose(1, 2).requires_grad_(True)
+    k = kvbuf[:, :D].float().reshape(B, Sk, H, 64).transpose(1, 2).requires_grad_(True)
+    v = kvbuf[:, D:].float().reshape(B, Sk, H, 64).transpose(1, 2).requires_grad_(True)
+    oref, _ = _attn_ref(q, k, v, causal, 0.125)
+    oref.backward(dout.float().view(B, Sq, H, 64).transpose(1, 2))
+    g = lambda t, S: t.float().reshape(B, S, H, 64).transpose(1, 2)
+    # P, dS and the outputs are rounded to bf16; D uses the bf16 forward output
+    assert rel_err(g(dq, Sq), q.grad) < 2e-2
+    assert rel_err(g(dkv[:, :D], Sk), k.grad) < 2e-2
+    assert rel_err(g(dkv[:, D:], Sk), v.grad) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------- layernorm
+@pytest.mark.parametrize("rows,dim,eps", [(1009, 768, 1e-6), (77, 1024, 1e-5), (5, 128, 1e-5)])
+def test_layernorm_fwd_bwd(cuda_lib, rows, dim, eps):
+    from pixparse_b200 import ops
+    torch.manual_seed(5)
+    x = (torch.randn((rows, dim), device=DEV) * 2 + 0.5)
+    g = torch.randn(dim, device=DEV)
+    b = torch.randn(dim, device=DEV)
+    y16, y32, mean, rstd = ops.layernorm_fwd(x, g, b, eps, want_f32=True)
+    xr = x.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    yref = F.layer_norm(xr, (dim,), gr, br, eps)
+    assert rel_err(y32, yref) < 1e-5
+    assert rel_err(y16, yref) < 4e-3
+    dy16 = torch.randn((rows, dim), device=DEV).bfloat16()
+    dy32 = torch.randn((rows, dim), device=DEV)
+    dres = torch.randn((rows, dim), device=DEV)
+    yref.backward(dy16.float() + dy32)
+    dgamma = torch.zeros(dim, device=DEV)
+    dbeta = torch.zeros(dim, device=DEV)
+    dx32, dx16 = ops.layernorm_bwd(x, mean, rstd, g, dgamma, dbeta, dy16=dy16, dy32=dy32, dres32=dres)
+    assert rel_err(dx32, xr.grad + dres) < 1e-4
+    assert rel_err(dx16, xr.grad + dres) < 4e-3
+    assert rel_err(dgamma, gr.grad) < 1e-4
+    assert rel_err(dbeta, br.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------- helpers
+def test_colsum(cuda_lib):
+    from pixparse_b200 import ops
+    torch.manual_seed(6)
+    dy = torch.randn((1009, 776), device=DEV).bfloat16()
+    out = torch.ones(776, device=DEV)
+    ops.colsum(dy, out)
+    assert rel_err(out, 1 + dy.float().sum(0)) < 1e-5
+
+
+def test_patch_unfold_and_assemble(cuda_lib):
+    from pixparse_b200 import ops
+    torch.manual_seed(7)
+    B, C, H, W, P, D = 2, 1, 64, 48, 16, 128
+    img = torch.randn((B, C, H, W), device=DEV)
+    patches = ops.patch_unfold(img, P)
+    ref = F.unfold(img, P, stride=P).transpose(1, 2).reshape(-1, C * P * P)
+    assert torch.equal(patches, ref.bfloat16())
+    S = (H // P) * (W // P) + 1
+    proj = torch.randn((B * (S - 1), D), device=DEV).bfloat16()
+    cls = torch.randn(D, device=DEV)
+    pos = torch.randn((S, D), device=DEV)
+    x = ops.tokens_assemble(proj, cls, pos, B, S, D)
+    xref = torch.cat([cls.expand(B, 1, D), proj.float().view(B, S - 1, D)], 1) + pos
+    assert torch.allclose(x.view(B, S, D), xref, atol=1e-6)
+    dx = torch.randn((B * S, D), device=DEV)
+    dcls = torch.zeros(D, device=DEV)
+    dpos = torch.zeros((S, D), device=DEV)
+    dproj = ops.tokens_assemble_bwd(dx, dcls, dpos, B, S, D)
+    d3 = dx.view(B, S, D)
+    assert torch.allclose(dpos, d3.sum(0), atol=1e-5)
+    assert torch.allclose(dcls, d3[:, 0].sum(0), atol=1e-5)
+    assert torch.equal(dproj.view(B, S - 1, D), d3[:, 1:].bfloat16())
+
+
+def test_embedding_fwd_bwd(cuda_lib):
+    from pixparse_b200 import ops
+    torch.manual_seed(8)
+    B, T, D, V = 3, 17, 128, 1000
+    ids = torch.randint(0, V, (B, T), device=DEV)
+    ids[0, -3:] = 1   # padding
+    tok = torch.randn((V, D), device=DEV)
+    pos = torch.randn((T + 2, D), device=DEV)
+    x = ops.embed_fwd(ids, tok, pos)
+    ref = tok[ids] + pos[torch.arange(T, device=DEV) + 2]
+    assert torch.allclose(x.view(B, T, D), ref, atol=1e-6)
+    dx = torch.randn((B * T, D), device=DEV)
+    dtok = torch.zeros_like(tok)
+    dpos = torch.zeros_like(pos)
+    ops.embed_bwd(ids, dx, dtok, dpos, padding_idx=1)
+    emb = torch.nn.Embedding(V, D, padding_idx=1).to(DEV)
+    emb.weight.data.copy_(tok)
+    emb(ids).backward(dx.view(B, T, D))
+    assert torch.allclose(dtok, emb.weight.grad, atol=1e-5)
+    assert torch.allclose(dpos[2:], dx.view(B, T, D).sum(0), atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,V", [(64, 50267), (33, 1003), (16, 50286)])
+def test_cross_entropy(cuda_lib, rows, V):
+    from pixparse_b200 import ops
+    torch.manual_seed(9)
+    ld = (V + 7) // 8 * 8
+    logits = torch.zeros((rows, ld), device=DEV, dtype=torch.bfloat16)
+    logits[:, :V] = (torch.randn((rows, V), device=DEV) * 3).bfloat16()
+    logits[:, V:] = 1000.0      # garbage in the padding must be ignored
+    tgt = torch.randint(0, V, (rows,), device=DEV)
+    tgt[::5] = -100
+    lf = logits[:, :V].float().requires_grad_(True)
+    ref = F.cross_entropy(lf, tgt, ignore_index=-100)
+    ref.backward()
+    dl = torch.empty_like(logits)
+    stats = ops.cross_entropy(logits, tgt, V, dlogits=dl)
+    assert stats[0].item() == (tgt != -100).sum().item()
+    assert abs(stats[1].item() - ref.item()) < 1e-4 * abs(ref.item())     # fp32 statistics over bf16 logits
+    assert rel_err(dl[:, :V], lf.grad) < 4e-3                             # bf16 rounding of the gradient
+
+
+def test_grad_norm_and_adamw(cuda_lib):
+    import numpy as np
+    from pixparse_b200 import ops
+    torch.manual_seed(10)
+    n = 1 << 20
+    p = torch.randn(n, device=DEV)
+    g = torch.randn(n, device=DEV) * 0.01
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    p16 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=3e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.0)
+    seg = np.zeros(1, dtype=[("end", "<i8"), ("lr_scale", "<f4"), ("wd", "<f4")])
+    seg["end"] = n; seg["lr_scale"] = 1.0; seg["wd"] = 0.0
+    segs = torch.from_numpy(seg.view(np.uint8)).to(DEV)
+    for step in (1, 2, 3):
+        g = torch.randn(n, device=DEV) * 0.01
+        pr.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_([pr], 1.0)
+        opt.step()
+        stats = ops.grad_norm(g, max_norm=1.0)
+        assert abs(stats[1].item() - total.item()) < 1e-5 * total.item()
+        ops.adamw_step(p, g, m, v, p16, segs, 1, lr=3e-4, beta1=0.9, beta2=0.98, eps=1e-6, step=step,
+                       norm_stats=stats)
+        assert (p - pr.detach()).abs().max().item() < 2e-6
+        assert torch.equal(p16, p.bfloat16())
+        assert g.abs().max().item() == 0.0      # zero_grad fused
