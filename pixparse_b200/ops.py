@@ -30,10 +30,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=Non
         M = a.shape[1] if a_mn else a.shape[0]
     if K is None:
         K = a.shape[0] if a_mn else a.shape[1]
+        kb = b.shape[0] if b_mn else b.shape[1]
+        assert kb == K, f"reduction dims differ: {K} vs {kb}"
     if N is None:
         N = b.shape[1] if b_mn else b.shape[0]
-    kb = b.shape[0] if b_mn else b.shape[1]
-    assert kb == K, f"reduction dims differ: {K} vs {kb}"
     if out is None:
         if epi in (EPI_RESID_F32, EPI_STORE_F32):
             out = torch.empty((M, N), device=a.device, dtype=F32)
@@ -114,11 +114,13 @@ def colsum(dy, out, rows=None, cols=None):
     call("b200_colsum_bf16", ptr(dy), _ld(dy), rows, cols, ptr(out), stream())
 
 
-def patch_unfold(image, P):
+def patch_unfold(image, P, ld=None):
     B, C, H, W = image.shape
     assert image.dtype == F32 and image.is_contiguous()
     n = B * (H // P) * (W // P)
-    patches = torch.empty((n, C * P * P), device=image.device, dtype=BF16)
+    K = C * P * P
+    # ld > K pads each row (TMA needs 16-byte row strides); the GEMM is told K, so the padding is never read
+    patches = torch.empty((n, ld or K), device=image.device, dtype=BF16)
     call("b200_patch_unfold", ptr(image), ptr(patches), B, C, H, W, P, patches.stride(0), stream())
     return patches
 
