@@ -95,7 +95,52 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per C-ABI call (grad_norm: partial + final; attention_bwd: prep + main + dq convert)
+_KERNELS_PER_CALL = {"b200_grad_norm": 2, "b200_attention_bwd": 3}
+_launches = 0
+_profile = None     # {name: [(start_event, end_event, flops), ...]} while profile_ops() is active
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
 def call(name, *args):
-    rc = getattr(lib(), name)(*args)
+    global _launches
+    prof = _profile
+    if prof is not None and name in prof:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        flops = 2.0 * args[6] * args[7] * args[8] if name == "b200_gemm_bf16" else 0.0
+        prof[name].append((e0, e1, flops))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         check(rc, name)
+    _launches += _KERNELS_PER_CALL.get(name, 1)
+
+
+def profile_ops(fn, names, repeats=1):
+    """Run fn() `repeats` times with CUDA events around every call of the named entry points (on the launch stream).
+    Returns {name: {"ms": device ms per repeat, "calls": launches per repeat, "flops": algorithmic FLOPs per repeat}}."""
+    global _profile
+    _profile = {n: [] for n in names}
+    try:
+        for _ in range(repeats):
+            fn()
+        torch.cuda.synchronize()
+        out = {}
+        for n, evs in _profile.items():
+            out[n] = {"ms": sum(a.elapsed_time(b) for a, b, _ in evs) / repeats, "calls": len(evs) // repeats,
+                      "flops": sum(f for _, _, f in evs) / repeats}
+        return out
+    finally:
+        _profile = None

@@ -55,3 +55,45 @@ def synthetic_batch(batch, image_size=(576, 448), text_len=513, vocab=PRETRAIN_V
     target[text == PAD_ID] = -100
     target[:, 0] = -100   # prompt_end_token == task_start_token at position 0 (data/preprocess.py:97-101)
     return image, text, target
+
+
+class SyntheticBartTokenizer:
+    """Tokenizer with facebook/bart-large's id layout (pad 1, eos 2, bos 0, 50265 entries) for offline runs: it can
+    add and look up special tokens, which is all the train step needs when the token ids are synthetic."""
+
+    def __init__(self):
+        self.pad_token_id, self.eos_token_id, self.bos_token_id, self.unk_token_id = PAD_ID, EOS_ID, 0, 3
+        self.pad_token, self.eos_token, self.bos_token = "<pad>", "</s>", "<s>"
+        self._size = BART_VOCAB
+        self._added = {}
+
+    def __len__(self):
+        return self._size
+
+    def add_special_tokens(self, d):
+        n = 0
+        for t in d.get("additional_special_tokens", []):
+            if t not in self._added:
+                self._added[t] = self._size
+                self._size += 1
+                n += 1
+        return n
+
+    def add_tokens(self, toks):
+        return self.add_special_tokens({"additional_special_tokens": list(toks)})
+
+    def convert_tokens_to_ids(self, t):
+        if isinstance(t, (list, tuple)):
+            return [self.convert_tokens_to_ids(x) for x in t]
+        base = {"<s>": 0, "<pad>": 1, "</s>": 2, "<unk>": 3}
+        return self._added.get(t, base.get(t, 3))
+
+    def encode(self, text, add_special_tokens=False):
+        return [self.convert_tokens_to_ids(text)]
+
+    def decode(self, ids, **kw):
+        inv = {v: k for k, v in self._added.items()}
+        return " ".join(inv.get(int(i), f"<{int(i)}>") for i in ids)
+
+    def batch_decode(self, batch, **kw):
+        return [self.decode(x) for x in batch]

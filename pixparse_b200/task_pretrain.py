@@ -1,0 +1,255 @@
+"""Cruller pre-training task on the B200-native path.
+
+Drop-in for ``pixparse.task.TaskCrullerPretrain`` (/root/reference/src/pixparse/task/task_cruller_pretrain.py:50-391):
+same constructor signature ``(cfg, device_env, monitor)``, same ``train_setup / train_interval_start / train_step /
+train_interval_end / state_dict / get_current_lr`` sequence, same attributes the app loop reads. What changes is what
+runs underneath ``train_step``:
+
+    reference                                            here
+    -------------------------------------------------   ----------------------------------------------------------
+    autocast + Cruller.forward (timm / transformers)     engine.forward_backward: tcgen05 GEMM / attention kernels
+    nn.CrossEntropyLoss on materialised fp32 logits      one-pass CE kernel writing dlogits in place (bf16)
+    scaler.scale(loss).backward() (autograd)             hand-sequenced backward kernels, fp32 grads in a flat arena
+    DDP reducer (25 MiB buckets)                         GradReducer: NCCL all-reduce of arena ranges under backward
+    GradScaler.unscale_ + clip_grad_norm_ + AdamW        grad_norm + fused clip/AdamW/bf16-refresh/zero-grad kernels
+
+Numerics are bf16 operands with fp32 accumulation and fp32 master weights, i.e. what the reference gets from
+``--task.dtype bfloat16``; no GradScaler is needed for bf16 (a non-finite gradient norm still skips the update,
+which is the observable effect the reference's scaler has).
+"""
+import logging
+from dataclasses import dataclass, field
+from functools import partial
+from typing import Optional
+
+import torch
+
+from .engine import engine_for
+from .framework import DeviceEnv, OptimizationCfg, TaskTrain, TaskTrainCfg
+from .models import Cruller, ModelCfg, get_model_config
+from .optim import FusedAdamW
+from .reducer import GradReducer
+from .schedule import create_scheduler
+from . import synthetic
+
+_logger = logging.getLogger(__name__)
+
+
+@dataclass
+class TokenizerCfg:
+    name: str = 'facebook/bart-large'
+    pretrained: bool = True
+
+
+@dataclass
+class TaskCrullerPretrainCfg(TaskTrainCfg):
+    model_name: Optional[str] = None
+    model: ModelCfg = field(default_factory=ModelCfg)
+    tokenizer: TokenizerCfg = field(default_factory=TokenizerCfg)
+
+    def __post_init__(self):
+        if self.model_name:
+            model = get_model_config(self.model_name)
+            if model is None:
+                _logger.warning(f'Model config for {self.model_name} was not found, using defaults.')
+            else:
+                self.model = model
+        else:
+            self.model_name = 'custom'
+
+
+def load_tokenizer(cfg: TokenizerCfg):
+    """HF AutoTokenizer when its files are reachable (tokenizers/tokenizer_hf.py:6-13); otherwise a tokenizer with
+    bart's id layout that can only map the special tokens (enough for synthetic-token training and benchmarks)."""
+    try:
+        from transformers import AutoTokenizer
+        return AutoTokenizer.from_pretrained(cfg.name)
+    except Exception as e:   # offline hub
+        _logger.warning(f"tokenizer {cfg.name} unavailable ({type(e).__name__}); using the synthetic bart-layout tokenizer")
+        return synthetic.SyntheticBartTokenizer()
+
+
+class _TokenizerHolder:
+    """Stand-in for pixparse.tokenizers.TokenizerHF: exposes ``.trunk``."""
+
+    def __init__(self, trunk):
+        self.trunk = trunk
+
+
+class TaskCrullerPretrain(TaskTrain):
+    def __init__(self, cfg: TaskCrullerPretrainCfg, device_env: DeviceEnv, monitor=None, tokenizer=None):
+        super().__init__(cfg=cfg, device_env=device_env, monitor=monitor)
+        self.cfg = cfg
+        self.amp_dtype = None
+        if cfg.dtype is not None:
+            self.amp_dtype = torch.bfloat16 if cfg.dtype in ('bfloat16', 'bf16') else torch.float16
+        if cfg.amp and self.amp_dtype is torch.float16:
+            raise ValueError("the B200 path computes in bf16; fp16 autocast + loss scaling is not implemented")
+
+        self.task_start_token = '<s_pretrain>'
+        self.prompt_end_token = self.task_start_token
+        self.max_position_embeddings = cfg.model.text_decoder.max_length
+        self.text_anno_fn = False
+        self.tokenizer = _TokenizerHolder(tokenizer if tokenizer is not None else load_tokenizer(cfg.tokenizer))
+
+        special_tokens = ["<sep/>", self.task_start_token, self.prompt_end_token]
+        newly_added_num = self.tokenizer.trunk.add_special_tokens(
+            {"additional_special_tokens": sorted(set(special_tokens))})
+        self.vocab_size = len(self.tokenizer.trunk)
+
+        self.anno_preprocess_train = partial(
+            preprocess_text_tokens, tokenizer=self.tokenizer.trunk,
+            max_position_embeddings=self.max_position_embeddings, task_start_token=self.task_start_token,
+            prompt_end_token=self.prompt_end_token)
+
+        cfg.model.image_encoder.pretrained = False     # no hub access: weights come from load_state_dict
+        cfg.model.text_decoder.pretrained = False
+        self.model = Cruller(cfg.model)
+        if newly_added_num > 0:
+            self.model.text_decoder.trunk.resize_token_embeddings(len(self.tokenizer.trunk))
+
+        self.has_no_sync = False
+        self.num_image_chs = 1 if cfg.model.image_encoder.image_fmt == 'L' else 3
+        img_mean = self.model.image_encoder.trunk.pretrained_cfg['mean']
+        img_std = self.model.image_encoder.trunk.pretrained_cfg['std']
+        self.img_mean = sum(img_mean) / len(img_mean) if cfg.model.image_encoder.image_fmt == 'L' else img_mean
+        self.img_std = sum(img_std) / len(img_std) if cfg.model.image_encoder.image_fmt == 'L' else img_std
+        self.image_preprocess_train = build_image_preprocess(
+            cfg.model.image_encoder.image_size, self.img_mean, self.img_std)
+        self.image_preprocess_eval = None
+        self.train_metrics = {}
+        self.eval_metrics = {}
+        self.max_recursion_length = 1000
+        self.engine = None
+        self.reducer = None
+        self.last_loss = None      # device tensor [n_valid, mean_loss] of the latest micro-step
+
+    # ------------------------------------------------------------------------------------------------------------
+    def train_setup(self, num_batches_per_interval: int):
+        device = self.device_env.device
+        self.model.to(device)
+        self.engine = engine_for(self.model)
+        arena = self.engine.ensure_bound()
+
+        if self.device_env.world_size > 1:
+            # all ranks start from rank 0's weights (DDP broadcasts parameters at construction)
+            torch.distributed.broadcast(arena.p32, src=0)
+            self.reducer = GradReducer(arena.g32)
+            self.has_no_sync = True
+
+            def _ready(first_key, last_key, _ar=arena, _r=self.reducer):
+                lo = _ar.index[first_key][0]
+                o, n, _ = _ar.index[last_key]
+                _r.range_ready(lo, o + (n + 63) // 64 * 64)
+            self.engine._grad_ready_hook = _ready
+
+        opt = self.cfg.opt
+        if opt.optimizer != 'adamw':
+            raise ValueError("only 'adamw' is on the Cruller hot path (framework/config.py:8)")
+        kw = {}
+        if opt.betas is not None:
+            kw['betas'] = tuple(opt.betas)
+        self.optimizer = FusedAdamW(self.model, self.engine, lr=opt.learning_rate, eps=opt.eps,
+                                    layer_decay=opt.layer_decay, **kw)
+        self.scaler = None          # bf16: no loss scaling
+        self.autocast = None
+        if opt.clip_grad_value is not None and (opt.clip_grad_mode or 'norm') != 'norm':
+            raise ValueError("only clip_grad_mode='norm' is fused on the B200 path")
+
+        self.num_steps_per_interval = num_batches_per_interval // opt.grad_accum_steps
+        self.scheduler, _ = create_scheduler(
+            self.optimizer, opt.scheduler, warmup_lr=opt.warmup_learning_rate,
+            warmup_intervals=self.num_warmup_intervals, num_intervals=self.num_intervals,
+            updates_per_interval=self.num_steps_per_interval)
+        self.scheduler.step_update(0)
+
+    def train_interval_start(self):
+        self.engine.zero_grads()
+        self.interval_batch_idx = 0
+
+    def train_interval_end(self):
+        if self.monitor is not None:
+            self.monitor.log_phase('train', self.interval_idx)
+        self.interval_idx += 1
+
+    def train_step(self, sample):
+        image_input, text_input, text_target = sample
+        result = {}
+        device = self.device_env.device
+        image_input = image_input.to(device, non_blocking=True)
+        text_input = text_input[:, :-1].to(device, non_blocking=True).contiguous()
+        text_target = text_target[:, 1:].to(device, non_blocking=True).contiguous()
+
+        accum_steps = self.cfg.opt.grad_accum_steps
+        need_update = (self.interval_batch_idx + 1) % accum_steps == 0
+
+        if self.reducer is not None:
+            self.reducer.enabled = need_update      # == model.no_sync() on accumulation micro-steps
+            self.reducer.begin()
+        self.last_loss = self.engine.forward_backward(image_input, text_input, text_target,
+                                                      grad_scale=1.0 / accum_steps)
+        if self.reducer is not None:
+            self.reducer.finish()
+
+        self.batch_idx += 1
+        self.interval_batch_idx += 1
+        if not need_update:
+            return result
+
+        self.optimizer.step(clip_grad_norm=self.cfg.opt.clip_grad_value)
+        self.step += 1
+        self.scheduler.step_update(self.step)
+        self.optimizer.zero_grad()
+
+        if self.step % self.eval_frequency == 0 and self.monitor is not None:
+            self.monitor.log_step(
+                'train', step_idx=self.step, step_end_idx=self.num_intervals * self.num_steps_per_interval,
+                interval=self.interval_idx, loss=self.last_loss[1].item() / accum_steps,
+                lr=self.get_current_lr(), metrics=self.train_metrics, eval_data=None)
+        return result
+
+    def eval_step(self, sample):
+        pass
+
+    def state_dict(self):
+        state_dicts = {'model': self.model.state_dict(), 'optimizer': self.optimizer.state_dict()}
+        if hasattr(self.scheduler, 'state_dict'):
+            state_dicts['scheduler'] = self.scheduler.state_dict()
+        return state_dicts
+
+    def load_state_dict(self, state_dict):
+        sd = state_dict.get('model', state_dict)
+        sd = {k.replace('module.', '', 1) if k.startswith('module.') else k: v for k, v in sd.items()}
+        self.model.load_state_dict(sd)
+        if 'optimizer' in state_dict and self.optimizer is not None:
+            self.optimizer.load_state_dict(state_dict['optimizer'])
+        if 'scheduler' in state_dict and self.scheduler is not None:
+            self.scheduler.load_state_dict(state_dict['scheduler'])
+
+    def __repr__(self):
+        return '\n'.join([f'model: {repr(self.model)}', f'opt: {repr(self.optimizer)}', f'sched: {repr(self.scheduler)}'])
+
+
+def build_image_preprocess(image_size, mean, std):
+    """The reference's CPU page preprocessing (task_cruller_pretrain.py:132-143): ToTensor -> bicubic antialiased
+    Resize (no aspect preservation) -> scalar Normalize. Runs in DataLoader workers, outside the GPU step."""
+    import torchvision.transforms as transforms
+    return transforms.Compose([
+        transforms.ToTensor(),
+        transforms.Resize(tuple(image_size), interpolation=transforms.InterpolationMode.BICUBIC, antialias=True),
+        transforms.Normalize(mean=mean, std=std),
+    ])
+
+
+def preprocess_text_tokens(anno, tokenizer, max_position_embeddings, task_start_token, prompt_end_token,
+                           ignore_id=-100, generator=None):
+    """Annotation -> (text ids, target ids), as data/preprocess.py:9-40 does for raw-text annotations:
+    pad to max length, PAD -> ignore_id, everything up to and including the prompt-end token -> ignore_id."""
+    text = task_start_token + anno + tokenizer.eos_token
+    ids = tokenizer(text, add_special_tokens=False, return_tensors='pt', max_length=max_position_embeddings,
+                    padding='max_length', truncation=True).input_ids[0]
+    target = ids.clone()
+    target[target == tokenizer.pad_token_id] = ignore_id
+    prompt_end_token_id = tokenizer.convert_tokens_to_ids(prompt_end_token)
+    target[:torch.nonzero(target == prompt_end_token_id).sum() + 1] = ignore_id
+    return dict(text=[ids], target=[target])

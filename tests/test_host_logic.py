@@ -1,0 +1,104 @@
+"""Host-side logic that needs no GPU: LR schedule, layer-decay grouping, multi-rank gradient reducer (gloo)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_cosine_schedule_matches_oracle_restatement():
+    from oracle import timm_helpers
+    from pixparse_b200.schedule import create_scheduler
+    p1 = [torch.nn.Parameter(torch.zeros(3))]
+    p2 = [torch.nn.Parameter(torch.zeros(3))]
+    o1 = torch.optim.AdamW([{"params": p1, "lr_scale": 0.5}], lr=3e-4)
+    o2 = torch.optim.AdamW([{"params": p2, "lr_scale": 0.5}], lr=3e-4)
+    s1, _ = create_scheduler(o1, 'cosine', warmup_lr=0.0, warmup_intervals=2, num_intervals=10, updates_per_interval=7)
+    s2, _ = timm_helpers.create_scheduler_v2(o2, 'cosine', warmup_lr=0.0, warmup_epochs=2, num_epochs=10,
+                                             step_on_epochs=False, updates_per_epoch=7)
+    for t in list(range(0, 30)) + [35, 69, 70, 71, 100]:
+        s1.step_update(t)
+        s2.step_update(t)
+        assert o1.param_groups[0]["lr"] == pytest.approx(o2.param_groups[0]["lr"], rel=1e-12, abs=1e-18)
+    s1.step_update(14)     # end of warm-up: the cosine is not shifted by the warm-up length
+    assert o1.param_groups[0]["lr"] == pytest.approx(0.5 * 0.5 * 3e-4 * (1 + math.cos(math.pi * 14 / 70)))
+
+
+def test_layer_decay_grouping_matches_oracle_restatement():
+    from oracle import timm_helpers
+    from pixparse_b200.optim import layer_decay_groups
+    m = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.LayerNorm(4), torch.nn.Linear(4, 2))
+    ours = layer_decay_groups(m, 0.75)
+    ref = timm_helpers.param_groups_layer_decay(m, weight_decay=0.0, layer_decay=0.75)
+    assert [(g["lr_scale"], len(g["params"])) for g in ours] == [(g["lr_scale"], len(g["params"])) for g in ref]
+    m.pretrained_cfg = {"classifier": "2."}          # a model that does name its head gets 12-tensor chunks
+    ours = layer_decay_groups(m, 0.75)
+    ref = timm_helpers.param_groups_layer_decay(m, weight_decay=0.0, layer_decay=0.75)
+    assert sorted((g["lr_scale"], len(g["params"])) for g in ours) == sorted((g["lr_scale"], len(g["params"])) for g in ref)
+
+
+def _reducer_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from pixparse_b200.framework import DeviceEnv
+    from pixparse_b200.reducer import GradReducer
+    env = DeviceEnv(device_type="cpu", backend="gloo")
+    assert (env.world_size, env.global_rank) == (world, rank)
+    n = 1000
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    red = GradReducer(flat, bucket_bytes=4 * 300)
+    # backward finishes ranges from the top of the arena downwards; the stem [0, 100) is never announced
+    red.begin()
+    red.range_ready(700, 1000)
+    red.range_ready(400, 700)
+    red.range_ready(100, 400)
+    red.finish()
+    expect = torch.arange(n, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    ok = torch.allclose(flat, expect)
+    covered = sorted(red._done)
+    ok = ok and covered[0][0] == 0 and covered[-1][1] == n
+    # accumulation micro-step: no_sync leaves local gradients untouched
+    flat2 = torch.full((n,), float(rank + 1))
+    red2 = GradReducer(flat2, bucket_bytes=1 << 20)
+    with red2.no_sync():
+        red2.begin()
+        red2.range_ready(0, n)
+        red2.finish()
+    ok = ok and torch.equal(flat2, torch.full((n,), float(rank + 1)))
+    red2.begin()
+    red2.range_ready(0, n)
+    red2.finish()
+    ok = ok and torch.allclose(flat2, torch.full((n,), (1 + world) / 2.0))
+    obj = env.broadcast_object({"x": 42} if rank == 0 else None)
+    ok = ok and obj == {"x": 42}
+    with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
+        f.write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_world_size_2_gloo(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_reducer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
+
+
+def test_synthetic_batch_layout():
+    from pixparse_b200 import synthetic
+    img, text, tgt = synthetic.synthetic_batch(3, (64, 48), 33, seed=1)
+    assert img.shape == (3, 1, 64, 48) and img.dtype == torch.float32 and img.min() >= -1 and img.max() <= 1
+    assert (text[:, 0] == synthetic.S_PRETRAIN_ID).all() and (tgt[:, 0] == -100).all()
+    for b in range(3):
+        eos = (text[b] == synthetic.EOS_ID).nonzero()[0, 0].item()
+        assert (text[b, eos + 1:] == synthetic.PAD_ID).all() and (tgt[b, eos + 1:] == -100).all()
+        assert (tgt[b, 1:eos + 1] == text[b, 1:eos + 1]).all()
+    img2, _, _ = synthetic.synthetic_batch(3, (64, 48), 33, seed=1)
+    assert torch.equal(img, img2)
+    pages = synthetic.synthetic_pages_u8(2, 110, 85, seed=0)
+    assert pages.dtype == torch.uint8 and pages.shape == (2, 110, 85)
