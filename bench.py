@@ -243,6 +243,8 @@ def run_b200_arm(args):
                 "traffic": None, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "launches_per_step": gemm_n, "gemm_ms_per_step": gemm_ms, "attention_ms_per_step": att_ms,
                 "share_of_step": gemm_ms / ms_step,
+                "by_variant": prof["b200_gemm_bf16"]["detail"],
+                "attention_fwd_ms": prof["b200_attention_fwd"]["ms"], "attention_bwd_ms": prof["b200_attention_bwd"]["ms"],
                 "how": "2 extra steps right after the timed region with CUDA events around each launch on the launch stream"}
 
     mfu_burst = pages_per_s * GFLOP_PER_PAGE / 1e3 / (world * peaks["bf16_burst"])

@@ -120,7 +120,8 @@ def call(name, *args):
         rc = getattr(lib(), name)(*args)
         e1.record()
         flops = 2.0 * args[6] * args[7] * args[8] if name == "b200_gemm_bf16" else 0.0
-        prof[name].append((e0, e1, flops))
+        tag = (f"gemm a_mn={args[2]} b_mn={args[5]} epi={args[9]}" if name == "b200_gemm_bf16" else name)
+        prof[name].append((e0, e1, flops, tag))
     else:
         rc = getattr(lib(), name)(*args)
     if rc != 0:
@@ -139,8 +140,16 @@ def profile_ops(fn, names, repeats=1):
         torch.cuda.synchronize()
         out = {}
         for n, evs in _profile.items():
-            out[n] = {"ms": sum(a.elapsed_time(b) for a, b, _ in evs) / repeats, "calls": len(evs) // repeats,
-                      "flops": sum(f for _, _, f in evs) / repeats}
+            detail = {}
+            for a, b, f, tag in evs:
+                d = detail.setdefault(tag, [0.0, 0.0, 0])
+                d[0] += a.elapsed_time(b) / repeats
+                d[1] += f / repeats
+                d[2] += 1
+            out[n] = {"ms": sum(a.elapsed_time(b) for a, b, _, _ in evs) / repeats, "calls": len(evs) // repeats,
+                      "flops": sum(f for _, _, f, _ in evs) / repeats,
+                      "detail": {t: {"ms": round(v[0], 3), "tflops": round(v[1] / (v[0] * 1e-3) / 1e12, 1) if v[0] > 0 and v[1] > 0 else None,
+                                     "calls": v[2] // repeats} for t, v in detail.items()}}
         return out
     finally:
         _profile = None

@@ -15,11 +15,12 @@
 
 namespace b200 {
 
-int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld);
+int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld, int box_rows);
 
 constexpr int AB_T = 128;                 // tile edge (queries and keys)
 constexpr int AB_D = 64;
-constexpr int AB_THREADS = 192;
+constexpr int AB_COMPUTE_THREADS = 256;   // 8 warps: warp w owns query rows 32*(w%4).., key columns 64*(w/4)..
+constexpr int AB_THREADS = AB_COMPUTE_THREADS + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB bf16 tile
 constexpr int AB_SMEM = 12 * AB_TILE + 256 + 1024;   // K, V, Q[2], dO[2], P(2), dS(2), dQ staging(2) = 192 KB
 
@@ -35,6 +36,11 @@ struct AttBwdParams {
   int q_col0, k_col0, v_col0, do_col0;
 };
 
+// Pipeline per query tile t (tensor pipe on the left, the 8 compute warps on the right run concurrently):
+//     S_t, dP_t ready ............ stage A: P_t = exp2(S_t*c - LSE)  -> smem, keeps P_t in registers
+//     dV += P_t^T dO_t ; S_{t+1} .. (drain dQ_{t-1}: TMEM -> smem -> TMA reduce-add) ; stage B: dS_t = P_t*(dP_t - D)*scale -> smem
+//     dK += dS_t^T Q_t ; dQ_t = dS_t K ; dP_{t+1} ....... stage A of tile t+1 ...
+// so the MMAs of one stage always run under the exp / multiply work of the other stage.
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -52,11 +58,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;    // [2]
   uint64_t* q_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* ps_full = bars + 6;
-  uint64_t* dq_full = bars + 7;
-  uint64_t* dkv_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* s_full = bars + 5;
+  uint64_t* dp_full = bars + 6;
+  uint64_t* p_ready = bars + 7;   // 256 arrivals: P_t in smem, S_t consumed
+  uint64_t* ds_ready = bars + 8;  // 256 arrivals: dS_t in smem, dP_t consumed
+  uint64_t* p_free = bars + 9;    // dV_t retired: P buffer reusable
+  uint64_t* dq_full = bars + 10;  // dK_t, dQ_t retired: dS buffer reusable, dQ_t readable
+  uint64_t* dkv_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,26 +82,29 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
   const int n_iter = q_tiles - i_begin;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_k);
     prefetch_tmap(&tmap_v);
     prefetch_tmap(&tmap_do);
     prefetch_tmap(&tmap_dq);
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
     }
-    mbar_init(sdp_full, 1);
-    mbar_init(ps_full, 128);
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(p_ready, AB_COMPUTE_THREADS);
+    mbar_init(ds_ready, AB_COMPUTE_THREADS);
+    mbar_init(p_free, 1);
     mbar_init(dq_full, 1);
     mbar_init(dkv_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
@@ -101,7 +113,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * AB_TILE);
@@ -117,7 +129,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tma_load_3d(sdO + s * AB_TILE, &tmap_do, &q_full[s], p.do_col0 + h * AB_D, q0, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0 && n_iter > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // S, dP
@@ -131,56 +143,93 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint64_t dP_mn = make_smem_desc(smem_u32(sP), 16384, 1024);    // P  as MN-major A (M = keys)
       const uint64_t dS_mn = make_smem_desc(smem_u32(sdS), 16384, 1024);   // dS as MN-major A (M = keys)
 
-      auto issue_s_dp = [&](int t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(&q_full[s], ph);
-        tc_fence_after();
-        const uint64_t dQ_k = make_smem_desc(smem_u32(sQ + s * AB_TILE), 16, 1024);
-        const uint64_t dO_k = make_smem_desc(smem_u32(sdO + s * AB_TILE), 16, 1024);
+      auto issue_s = [&](int t) {
+        const uint64_t dQ_k = make_smem_desc(smem_u32(sQ + (t & 1) * AB_TILE), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss(tmem_base + TB_S, dQ_k + (uint64_t)(2 * k), dK_k + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      auto issue_dp = [&](int t) {
+        const uint64_t dO_k = make_smem_desc(smem_u32(sdO + (t & 1) * AB_TILE), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss(tmem_base + TB_DP, dO_k + (uint64_t)(2 * k), dV_k + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(sdp_full);
+        umma_commit(dp_full);
       };
 
-      issue_s_dp(0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      issue_dp(0);
       for (int t = 0; t < n_iter; ++t) {
         const int s = t & 1;
-        mbar_wait(ps_full, t & 1);
-        tc_fence_after();
         const uint64_t dO_mn = make_smem_desc(smem_u32(sdO + s * AB_TILE), 16384, 1024);
         const uint64_t dQ_mn = make_smem_desc(smem_u32(sQ + s * AB_TILE), 16384, 1024);
-        // dV += P^T dO ; dK += dS^T Q    (reduction over the 128 queries, 16 per UMMA)
+        // ---- P_t ready: dV += P_t^T dO_t, then S_{t+1}
+        mbar_wait(p_ready, t & 1);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tmem_base + TB_DV, dP_mn + (uint64_t)(128 * k), dO_mn + (uint64_t)(128 * k), idesc_t,
                   (t > 0 || k > 0) ? 1u : 0u);
+        umma_commit(p_free);
+        if (t + 1 < n_iter) {
+          mbar_wait(&q_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(t + 1);
+        }
+        // ---- dS_t ready: dK += dS_t^T Q_t, dQ_t = dS_t K, then dP_{t+1}
+        mbar_wait(ds_ready, t & 1);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tmem_base + TB_DK, dS_mn + (uint64_t)(128 * k), dQ_mn + (uint64_t)(128 * k), idesc_t,
                   (t > 0 || k > 0) ? 1u : 0u);
-        // dQ = dS K    (reduction over the 128 keys; dS read K-major: 64-key chunk = k / 4, 32 B per step inside)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
+          // dS read K-major: 64-key chunk = k / 4, 32 bytes per step inside the 128-byte row
           const uint64_t dS_k = make_smem_desc(smem_u32(sdS + (k >> 2) * AB_TILE + (k & 3) * 32), 16, 1024);
           umma_ss(tmem_base + TB_DQ, dS_k, dK_mn + (uint64_t)(128 * k), idesc_q, k > 0 ? 1u : 0u);
         }
-        umma_commit(&q_empty[s]);
         umma_commit(dq_full);
-        if (t + 1 < n_iter) issue_s_dp(t + 1);
+        umma_commit(&q_empty[s]);
+        if (t + 1 < n_iter) issue_dp(t + 1);
       }
       umma_commit(dkv_full);
     }
   } else {
-    // ===================== compute warps: one query row per thread =====================
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ===================== compute warps =====================
+    const int half = warp >> 2;                 // key-column half of S / dP, d-column half of dQ / dK / dV
+    const int row = (warp & 3) * 32 + lane;     // TMEM lane = query row (S, dP, dQ) or key row (dK, dV)
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int sw = row & 7;
+    const int ht = threadIdx.x & 127;           // thread index inside the half group
     const float kLog2e = 1.4426950408889634f;
+    uint8_t* stage = sStage + half * AB_TILE;
+
+    auto drain_dq = [&](int t) {
+      // dQ_t columns [32*half, 32*half+32): TMEM -> swizzled fp32 staging -> TMA reduce-add (fp32 accumulator in HBM)
+      mbar_wait(dq_full, t & 1);
+      tc_fence_after();
+      if (ht == 0) tma_wait_group_read<0>();     // previous reduce of this half has finished reading the staging tile
+      named_bar_sync(1 + half, 128);
+      uint32_t r[32];
+      tmem_ld_32x32(lane_addr + TB_DQ + half * 32, r);
+      tmem_ld_wait();
+      uint8_t* rowp = stage + row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(1 + half, 128);
+      if (ht == 0) {
+        tma_reduce_add_3d(&tmap_dq, stage, h * AB_D + half * 32, (i_begin + t) * AB_T, b);
+        tma_commit_group();
+      }
+    };
+
     for (int t = 0; t < n_iter; ++t) {
       const int q0 = (i_begin + t) * AB_T;
       const int qidx = q0 + row;
@@ -191,124 +240,128 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int kmax = p.Sk - 1;
       if (p.causal) kmax = min(kmax, qidx + shift);
       const bool need_mask = (k0 + AB_T > p.Sk) || (p.causal && (k0 + AB_T - 1 > q0 + shift));
-      mbar_wait(sdp_full, t & 1);
+      const int kbase = k0 + half * 64;
+
+      // ---------------- stage A: P_t ----------------
+      float pv[64];
+      mbar_wait(s_full, t & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rp[32];
-        tmem_ld_32x32(lane_addr + TB_S + c * 32, rs);
-        tmem_ld_32x32(lane_addr + TB_DP + c * 32, rp);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rs[32];
+        tmem_ld_32x32(lane_addr + TB_S + half * 64 + c * 32, rs);
         tmem_ld_wait();
-        uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float p0 = exp2f(fmaf(__uint_as_float(rs[2 * e]), p.scale_log2, -lse2));
-          float p1 = exp2f(fmaf(__uint_as_float(rs[2 * e + 1]), p.scale_log2, -lse2));
-          if (need_mask) {
-            if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
-            if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
-          }
-          const float d0 = p0 * (__uint_as_float(rp[2 * e]) - dsum) * p.scale;
-          const float d1 = p1 * (__uint_as_float(rp[2 * e + 1]) - dsum) * p.scale;
-          pk[e] = pack_bf16(p0, p1);
-          dk[e] = pack_bf16(d0, d1);
+        for (int e = 0; e < 32; ++e) {
+          float v = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
+          if (need_mask && (kbase + c * 32 + e > kmax)) v = 0.f;
+          pv[c * 32 + e] = v;
         }
-        // keys [c*32, c*32+32) of this row: 64-key chunk c/2, 16-byte pieces (c%2)*4 .. +3, 128B-swizzled
-        uint8_t* prow = sP + (c >> 1) * AB_TILE + row * 128;
-        uint8_t* drow = sdS + (c >> 1) * AB_TILE + row * 128;
+      }
+      if (t > 0) mbar_wait(p_free, (t - 1) & 1);      // dV_{t-1} no longer reads the P buffer
+      {
+        uint8_t* prow = sP + half * AB_TILE + row * 128;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int piece = ((c & 1) * 4 + jj) ^ sw;
-          *reinterpret_cast<uint4*>(prow + (piece << 4)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          *reinterpret_cast<uint4*>(drow + (piece << 4)) = make_uint4(dk[4 * jj], dk[4 * jj + 1], dk[4 * jj + 2], dk[4 * jj + 3]);
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(prow + ((j ^ sw) << 4)) =
+              make_uint4(pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
+                         pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
       }
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(ps_full);
+      mbar_arrive(p_ready);
 
-      // ---- drain dQ_t: TMEM -> swizzled fp32 staging -> TMA reduce-add into the fp32 dQ accumulator
-      mbar_wait(dq_full, t & 1);
+      // ---------------- dQ of the previous tile leaves while the tensor pipe works on dV_t / S_{t+1} ------------
+      if (t > 0) drain_dq(t - 1);       // also guarantees dK_{t-1} / dQ_{t-1} no longer read the dS buffer
+
+      // ---------------- stage B: dS_t ----------------
+      mbar_wait(dp_full, t & 1);
       tc_fence_after();
-      if (threadIdx.x == 0) tma_wait_group_read<0>();   // staging buffers no longer read by the previous reduce
-      named_bar_sync(1, 128);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_addr + TB_DQ + c * 32, r);
-        tmem_ld_wait();
-        uint8_t* rowp = sStage + c * AB_TILE + row * 128;
+      {
+        uint8_t* drow = sdS + half * AB_TILE + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 0) {
-        tma_reduce_add_3d(&tmap_dq, sStage, h * AB_D, q0, b);
-        tma_reduce_add_3d(&tmap_dq, sStage + AB_TILE, h * AB_D + 32, q0, b);
-        tma_commit_group();
-      }
-    }
-    // ---- final: dK, dV (rows = keys of this tile) -> bf16 -> global
-    if (n_iter > 0) {
-      mbar_wait(dkv_full, 0);
-      tc_fence_after();
-    }
-    const int kidx = k0 + row;
-    const bool k_ok = kidx < p.Sk;
-    bf16* dkrow = p.dk + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dk + p.dk_col0 + h * AB_D;
-    bf16* dvrow = p.dv + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dv + p.dv_col0 + h * AB_D;
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      bf16* orow = which == 0 ? dvrow : dkrow;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        if (n_iter > 0) {
-          tmem_ld_32x32(lane_addr + (which == 0 ? TB_DV : TB_DK) + c * 32, r);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t rp[32];
+          tmem_ld_32x32(lane_addr + TB_DP + half * 64 + c * 32, rp);
           tmem_ld_wait();
-        } else {
+          float dsv[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) r[e] = 0u;
-        }
-        if (k_ok) {
+          for (int e = 0; e < 32; ++e) dsv[e] = pv[c * 32 + e] * (__uint_as_float(rp[e]) - dsum) * p.scale;
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(r[8 * v4 + 0]), __uint_as_float(r[8 * v4 + 1]));
-            o.y = pack_bf16(__uint_as_float(r[8 * v4 + 2]), __uint_as_float(r[8 * v4 + 3]));
-            o.z = pack_bf16(__uint_as_float(r[8 * v4 + 4]), __uint_as_float(r[8 * v4 + 5]));
-            o.w = pack_bf16(__uint_as_float(r[8 * v4 + 6]), __uint_as_float(r[8 * v4 + 7]));
-            *reinterpret_cast<uint4*>(orow + c * 32 + v4 * 8) = o;
+          for (int jj = 0; jj < 4; ++jj) {
+            const int piece = (c * 4 + jj) ^ sw;
+            *reinterpret_cast<uint4*>(drow + (piece << 4)) =
+                make_uint4(pack_bf16(dsv[8 * jj], dsv[8 * jj + 1]), pack_bf16(dsv[8 * jj + 2], dsv[8 * jj + 3]),
+                           pack_bf16(dsv[8 * jj + 4], dsv[8 * jj + 5]), pack_bf16(dsv[8 * jj + 6], dsv[8 * jj + 7]));
           }
         }
       }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
     }
-    if (threadIdx.x == 0) tma_wait_group<0>();
+    if (n_iter > 0) {
+      drain_dq(n_iter - 1);
+      mbar_wait(dkv_full, 0);
+      tc_fence_after();
+    }
+    // ---- final: dK, dV (rows = keys of this tile; this thread owns d columns [32*half, 32*half+32)) -> bf16 -> global
+    const int kidx = k0 + row;
+    const bool k_ok = kidx < p.Sk;
+    bf16* dkrow = p.dk + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dk + p.dk_col0 + h * AB_D + half * 32;
+    bf16* dvrow = p.dv + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dv + p.dv_col0 + h * AB_D + half * 32;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      bf16* orow = which == 0 ? dvrow : dkrow;
+      uint32_t r[32];
+      if (n_iter > 0) {
+        tmem_ld_32x32(lane_addr + (which == 0 ? TB_DV : TB_DK) + half * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = 0u;
+      }
+      if (k_ok) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[8 * v4 + 0]), __uint_as_float(r[8 * v4 + 1]));
+          o.y = pack_bf16(__uint_as_float(r[8 * v4 + 2]), __uint_as_float(r[8 * v4 + 3]));
+          o.z = pack_bf16(__uint_as_float(r[8 * v4 + 4]), __uint_as_float(r[8 * v4 + 5]));
+          o.w = pack_bf16(__uint_as_float(r[8 * v4 + 6]), __uint_as_float(r[8 * v4 + 7]));
+          *reinterpret_cast<uint4*>(orow + v4 * 8) = o;
+        }
+      }
+    }
+    if (ht == 0) tma_wait_group<0>();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem_base);
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
-// D[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per (b,q,h) row of 64 elements)
+// D[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (8 threads x 16 bytes per (b,q,h) row of 64 elements; coalesced)
 __global__ void attention_bwd_prep_kernel(const bf16* __restrict__ o, long long ld_o, const bf16* __restrict__ d_o,
                                           long long ld_do, int do_col0, float* __restrict__ dsum, int B, int H,
                                           int Sq) {
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)B * Sq * H;
-  for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
-       w += ((long long)gridDim.x * blockDim.x) >> 5) {
+  const long long total = (long long)B * Sq * H * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {      // total and the stride are multiples of 8: groups stay intact
+    const int part = (int)(idx & 7);
+    const long long w = idx >> 3;
     const int hh = (int)(w % H);
     const long long bq = w / H;     // b * Sq + q
-    const uint32_t a = *reinterpret_cast<const uint32_t*>(o + bq * ld_o + hh * 64 + lane * 2);
-    const uint32_t g = *reinterpret_cast<const uint32_t*>(d_o + bq * ld_do + do_col0 + hh * 64 + lane * 2);
-    float s = bf16_lo(a) * bf16_lo(g) + bf16_hi(a) * bf16_hi(g);
-    s = warp_sum(s);
-    if (lane == 0) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + bq * ld_o + hh * 64 + part * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(d_o + bq * ld_do + do_col0 + hh * 64 + part * 8);
+    float s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+              bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+              bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+    const uint32_t gmask = 0xFFu << (threadIdx.x & 24);   // the 8 lanes of this row (a warp's tail may be idle)
+    s += __shfl_xor_sync(gmask, s, 1);
+    s += __shfl_xor_sync(gmask, s, 2);
+    s += __shfl_xor_sync(gmask, s, 4);
+    if (part == 0) {
       const int bb = (int)(bq / Sq), q = (int)(bq % Sq);
       dsum[((long long)bb * H + hh) * Sq + q] = s;
     }
@@ -361,8 +414,8 @@ extern "C" int b200_attention_bwd(const void* q, long long ldq, int q_col0, cons
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(dq32)");
 
   {
-    const long long warps = (long long)B * Sq * H;
-    long long blocks = (warps * 32 + 255) / 256;
+    const long long items = (long long)B * Sq * H * 8;
+    long long blocks = (items + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     attention_bwd_prep_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(o), ld_o,
@@ -373,10 +426,10 @@ extern "C" int b200_attention_bwd(const void* q, long long ldq, int q_col0, cons
 
   CUtensorMap tq, tk, tv, tdo, tdq;
   int rc;
-  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)W, ldq))) return rc;
-  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)W, ldk))) return rc;
-  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)W, ldv))) return rc;
-  if ((rc = make_att_tmap(&tdo, d_o, B, Sq, do_col0 + (long long)W, ld_do))) return rc;
+  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)W, ldq, 128))) return rc;
+  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)W, ldk, 128))) return rc;
+  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)W, ldv, 128))) return rc;
+  if ((rc = make_att_tmap(&tdo, d_o, B, Sq, do_col0 + (long long)W, ld_do, 128))) return rc;
   {
     // fp32 dQ accumulator viewed as [B][Sq][W]; box = 32 floats x 128 rows (rows beyond Sq are clipped)
     uint64_t dims[3] = {(uint64_t)W, (uint64_t)Sq, (uint64_t)B};

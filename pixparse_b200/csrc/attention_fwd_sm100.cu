@@ -5,8 +5,9 @@
 //                    tcgen05.st back into TMEM (P never touches shared memory)
 //   O += P V         tcgen05.mma  (A = P from TMEM, B = V tile MN-major in shared memory)         -> TMEM
 //
-// One CTA per (128-query tile, head, batch); two CTAs are co-resident per SM (80 KB smem, 256 TMEM columns each)
-// so the MMA phases of one overlap the softmax phase of the other.
+// One CTA per (128-query tile, head, batch) walks the keys 64 at a time; P aliases the first half of S's TMEM columns,
+// so a CTA needs only 128 TMEM columns and 48 KB of shared memory: FOUR CTAs are co-resident per SM (16 softmax warps)
+// and the MMA / TMA / barrier latencies of one CTA hide under the exp2 work of the others.
 //
 // Serves the three attention shapes of the Cruller step:
 //   encoder self-attention (non-causal, Sq = Sk = 1009 / 2509), decoder causal self-attention (Sq = Sk = T),
@@ -18,15 +19,18 @@
 namespace b200 {
 
 constexpr int ATT_BM = 128;   // queries per CTA
-constexpr int ATT_BN = 128;   // keys per inner tile
+constexpr int ATT_BN = 64;    // keys per inner tile
 constexpr int ATT_D = 64;     // head dim
 constexpr int ATT_THREADS = 192;
-constexpr int ATT_TILE_BYTES = 128 * ATT_D * 2;   // 16 KB
-constexpr int ATT_SMEM = ATT_TILE_BYTES * 5 + 256 + 1024;
+constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;    // 16 KB
+constexpr int ATT_KV_BYTES = ATT_BN * ATT_D * 2;   // 8 KB
+constexpr int ATT_SMEM = ATT_Q_BYTES + 4 * ATT_KV_BYTES + 256 + 1024;
+constexpr int ATT_TMEM_COLS = 128;
 
-constexpr uint32_t TM_S = 0;      // 128 columns: S (fp32)
-constexpr uint32_t TM_P = 128;    // 64 columns:  P (bf16 pairs)
-constexpr uint32_t TM_O = 192;    // 64 columns:  O (fp32)
+constexpr uint32_t TM_S = 0;      // 64 columns: S (fp32)
+constexpr uint32_t TM_P = 0;      // 32 columns: P (bf16 pairs) -- aliases S: chunk c of P only overwrites S columns
+                                  //             that were already consumed; S_{j+1} is issued behind P_j V in order
+constexpr uint32_t TM_O = 64;     // 64 columns: O (fp32)
 
 struct AttFwdParams {
   int B, H, Sq, Sk;
@@ -38,15 +42,15 @@ struct AttFwdParams {
   int q_col0, k_col0, v_col0;   // column offsets of head 0 inside the Q / K / V row
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + ATT_TILE_BYTES;          // 2 stages
-  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;      // 2 stages
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
+  uint8_t* sK = smem + ATT_Q_BYTES;                       // 2 stages
+  uint8_t* sV = smem + ATT_Q_BYTES + 2 * ATT_KV_BYTES;    // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_Q_BYTES + 4 * ATT_KV_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;     // [2]
   uint64_t* v_full = bars + 3;     // [2]
@@ -88,7 +92,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     fence_mbar_init();
   }
   if (warp == 5) {
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -99,16 +103,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      mbar_expect_tx(q_full, ATT_Q_BYTES);
       tma_load_3d(sQ, &tmap_q, q_full, p.q_col0 + h * ATT_D, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sK + s * ATT_TILE_BYTES, &tmap_k, &k_full[s], p.k_col0 + h * ATT_D, j * ATT_BN, b);
-        mbar_expect_tx(&v_full[s], ATT_TILE_BYTES);
-        tma_load_3d(sV + s * ATT_TILE_BYTES, &tmap_v, &v_full[s], p.v_col0 + h * ATT_D, j * ATT_BN, b);
+        mbar_expect_tx(&k_full[s], ATT_KV_BYTES);
+        tma_load_3d(sK + s * ATT_KV_BYTES, &tmap_k, &k_full[s], p.k_col0 + h * ATT_D, j * ATT_BN, b);
+        mbar_expect_tx(&v_full[s], ATT_KV_BYTES);
+        tma_load_3d(sV + s * ATT_KV_BYTES, &tmap_v, &v_full[s], p.v_col0 + h * ATT_D, j * ATT_BN, b);
       }
     }
   } else if (warp == 5) {
@@ -123,7 +127,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_full[s], ph);
         tc_fence_after();
-        const uint64_t dk = make_smem_desc(smem_u32(sK + s * ATT_TILE_BYTES), 16, 1024);
+        const uint64_t dk = make_smem_desc(smem_u32(sK + s * ATT_KV_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k)
           umma_ss(tmem_base + TM_S, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
@@ -132,7 +136,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_wait(p_full, j & 1);
         mbar_wait(&v_full[s], ph);
         tc_fence_after();
-        const uint64_t dv = make_smem_desc(smem_u32(sV + s * ATT_TILE_BYTES), 16, 1024);
+        const uint64_t dv = make_smem_desc(smem_u32(sV + s * ATT_KV_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)
           umma_ts(tmem_base + TM_O, tmem_base + TM_P + 8 * k, dv + (uint64_t)(128 * k), idesc_o,
@@ -174,7 +178,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // fully masked so far: keep exp2 finite
-      const float alpha = exp2f(m_run - m_use);                  // 0 on the first tile (m_run = -inf)
+      const float alpha = ex2_approx(m_run - m_use);                  // 0 on the first tile (m_run = -inf)
       // ---- rescale the running O (TMEM) once the previous P V has retired
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
@@ -208,8 +212,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          float p0 = exp2f(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_use));
-          float p1 = exp2f(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_use));
+          float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_use));
+          float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_use));
           if (need_mask) {
             if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
             if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
@@ -255,14 +259,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<256>(tmem_base);
+  if (warp == 5) tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
 }
 
-// 3-D tensor map over a [B, S, width] bf16 activation whose rows are `ld` elements apart; box = 64 x 128 x 1
-int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld) {
+// 3-D tensor map over a [B, S, width] bf16 activation whose rows are `ld` elements apart; box = 64 x box_rows x 1
+int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld, int box_rows) {
   uint64_t dims[3] = {(uint64_t)width, (uint64_t)S, (uint64_t)B};
   uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)S};
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return make_tmap(m, base, TMA_BF16, 3, dims, strides, box, TMA_SWIZZLE_128B);
 }
 
@@ -283,9 +287,9 @@ extern "C" int b200_attention_fwd(const void* q, long long ldq, int q_col0, cons
   if (causal) B200_CHECK_ARG(Sk >= Sq, "b200_attention_fwd: causal attention needs Sk >= Sq");
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)H * ATT_D, ldq))) return rc;
-  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)H * ATT_D, ldk))) return rc;
-  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)H * ATT_D, ldv))) return rc;
+  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)H * ATT_D, ldq, ATT_BM))) return rc;
+  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)H * ATT_D, ldk, ATT_BN))) return rc;
+  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)H * ATT_D, ldv, ATT_BN))) return rc;
   AttFwdParams p;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
