@@ -114,24 +114,28 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * AB_TILE);
       tma_load_3d(sK, &tmap_k, kv_full, p.k_col0 + h * AB_D, k0, b);
       tma_load_3d(sV, &tmap_v, kv_full, p.v_col0 + h * AB_D, k0, b);
-      for (int t = 0; t < n_iter; ++t) {
-        const int s = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        const int q0 = (i_begin + t) * AB_T;
-        mbar_wait(&q_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    for (int t = 0; t < n_iter; ++t) {
+      const int s = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      const int q0 = (i_begin + t) * AB_T;
+      mbar_wait(&q_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&q_full[s], 2 * AB_TILE);
         tma_load_3d(sQ + s * AB_TILE, &tmap_q, &q_full[s], p.q_col0 + h * AB_D, q0, b);
         tma_load_3d(sdO + s * AB_TILE, &tmap_do, &q_full[s], p.do_col0 + h * AB_D, q0, b);
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && n_iter > 0) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    if (n_iter > 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // S, dP
       constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);      // dV, dK (A = P^T / dS^T)
       constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);     // dQ
@@ -145,17 +149,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
       auto issue_s = [&](int t) {
         const uint64_t dQ_k = make_smem_desc(smem_u32(sQ + (t & 1) * AB_TILE), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + TB_S, dQ_k + (uint64_t)(2 * k), dK_k + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem_base + TB_S, dQ_k + (uint64_t)(2 * k), dK_k + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       };
       auto issue_dp = [&](int t) {
         const uint64_t dO_k = make_smem_desc(smem_u32(sdO + (t & 1) * AB_TILE), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(tmem_base + TB_DP, dO_k + (uint64_t)(2 * k), dV_k + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(dp_full);
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem_base + TB_DP, dO_k + (uint64_t)(2 * k), dV_k + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(dp_full);
+        }
+        __syncwarp();
       };
 
       mbar_wait(&q_full[0], 0);
@@ -169,11 +179,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // ---- P_t ready: dV += P_t^T dO_t, then S_{t+1}
         mbar_wait(p_ready, t & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tmem_base + TB_DV, dP_mn + (uint64_t)(128 * k), dO_mn + (uint64_t)(128 * k), idesc_t,
-                  (t > 0 || k > 0) ? 1u : 0u);
-        umma_commit(p_free);
+          for (int k = 0; k < 8; ++k)
+            umma_ss(tmem_base + TB_DV, dP_mn + (uint64_t)(128 * k), dO_mn + (uint64_t)(128 * k), idesc_t,
+                    (t > 0 || k > 0) ? 1u : 0u);
+          umma_commit(p_free);
+        }
+        __syncwarp();
         if (t + 1 < n_iter) {
           mbar_wait(&q_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
           tc_fence_after();
@@ -182,21 +195,26 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // ---- dS_t ready: dK += dS_t^T Q_t, dQ_t = dS_t K, then dP_{t+1}
         mbar_wait(ds_ready, t & 1);
         tc_fence_after();
+        // dS read K-major for dQ: 64-key chunk = k / 4, 32 bytes per step inside the 128-byte row
+        const uint64_t dS_k0 = make_smem_desc(smem_u32(sdS), 16, 1024);
+        const uint64_t dS_k1 = make_smem_desc(smem_u32(sdS + AB_TILE), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tmem_base + TB_DK, dS_mn + (uint64_t)(128 * k), dQ_mn + (uint64_t)(128 * k), idesc_t,
-                  (t > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            umma_ss(tmem_base + TB_DK, dS_mn + (uint64_t)(128 * k), dQ_mn + (uint64_t)(128 * k), idesc_t,
+                    (t > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // dS read K-major: 64-key chunk = k / 4, 32 bytes per step inside the 128-byte row
-          const uint64_t dS_k = make_smem_desc(smem_u32(sdS + (k >> 2) * AB_TILE + (k & 3) * 32), 16, 1024);
-          umma_ss(tmem_base + TB_DQ, dS_k, dK_mn + (uint64_t)(128 * k), idesc_q, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)
+            umma_ss(tmem_base + TB_DQ, (k < 4 ? dS_k0 : dS_k1) + (uint64_t)(2 * (k & 3)), dK_mn + (uint64_t)(128 * k),
+                    idesc_q, k > 0 ? 1u : 0u);
+          umma_commit(dq_full);
+          umma_commit(&q_empty[s]);
         }
-        umma_commit(dq_full);
-        umma_commit(&q_empty[s]);
+        __syncwarp();
         if (t + 1 < n_iter) issue_dp(t + 1);
       }
-      umma_commit(dkv_full);
+      if (elect_one()) umma_commit(dkv_full);
+      __syncwarp();
     }
   } else {
     // ===================== compute warps =====================

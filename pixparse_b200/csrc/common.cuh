@@ -213,6 +213,23 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// same, into elements [OFF, OFF+32) of a larger register array (keeps the array in registers: no pointer casts)
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld_32x32_at(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(OFF + 32 <= N, "out of range");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]),
+        "=r"(r[OFF + 6]), "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]),
+        "=r"(r[OFF + 12]), "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15]), "=r"(r[OFF + 16]),
+        "=r"(r[OFF + 17]), "=r"(r[OFF + 18]), "=r"(r[OFF + 19]), "=r"(r[OFF + 20]), "=r"(r[OFF + 21]),
+        "=r"(r[OFF + 22]), "=r"(r[OFF + 23]), "=r"(r[OFF + 24]), "=r"(r[OFF + 25]), "=r"(r[OFF + 26]),
+        "=r"(r[OFF + 27]), "=r"(r[OFF + 28]), "=r"(r[OFF + 29]), "=r"(r[OFF + 30]), "=r"(r[OFF + 31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -271,20 +288,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Exact-erf GELU (timm nn.GELU / BART "gelu") evaluated with the Abramowitz-Stegun 7.1.26 rational form of erf
-// (|abs err| < 1.5e-7, far below bf16 resolution): 2 MUFU + ~10 FMA instead of the ~25-instruction erff().
-//   z = |x| / sqrt(2), t = 1 / (1 + p z), E = exp(-z^2) = exp(-x^2 / 2), erf(z) = 1 - poly(t) * E
+// Exact-erf GELU (timm nn.GELU / BART "gelu"): x * Phi(x), with the normal CDF from Abramowitz-Stegun 26.2.17
+// (|abs err| < 7.5e-8, far below bf16 resolution): 2 MUFU + ~10 FMA-pipe ops instead of the ~25-instruction erff().
+//   t = 1 / (1 + 0.2316419 |x|),  E = exp(-x^2 / 2),  1 - Phi(|x|) = E * t * (c1 + t (c2 + t (c3 + t (c4 + t c5))))
+//   with c_i = b_i / sqrt(2 pi)
 __device__ __forceinline__ void gelu_terms(float x, float& cdf, float& E) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  E = ex2_approx(-1.4426950408889634f * z * z);
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  const float half_erfc = 0.5f * poly * E;                  // 0.5 * (1 - erf(z))
-  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;            // Phi(x)
+  const float t = rcp_approx(fmaf(0.2316419f, fabsf(x), 1.0f));
+  E = ex2_approx(x * x * -0.72134752044448170f);            // exp(-x^2/2) = 2^(-x^2 * log2(e) / 2)
+  float poly = fmaf(t, 0.5307027145f, -0.7265760135f);
+  poly = fmaf(t, poly, 0.7107068705f);
+  poly = fmaf(t, poly, -0.1422483683f);
+  poly = fmaf(t, poly, 0.1274147959f);
+  const float tail = poly * t * E;                          // 1 - Phi(|x|)
+  cdf = x >= 0.f ? 1.0f - tail : tail;                      // Phi(x)
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float cdf, E;

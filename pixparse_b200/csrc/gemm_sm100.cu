@@ -10,8 +10,10 @@
 //   dgrad    dx = dy W        : A = dy [M,N'] K-major,  B = W  [N',K'] MN-major   (reduction dim is the row index)
 //   wgrad    dW = dy^T x      : A = dy [M',N] MN-major, B = x  [M',K] MN-major    (split-K, TMA reduce-add to fp32)
 //
-// Warp roles (384 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
-// warps4-7 / warps8-11 = two epilogue groups that take alternating 32-column chunks of the accumulator.
+// Warp roles (384 threads): warps0-3 / warps4-7 = two epilogue groups that take alternating 32-column chunks of the
+// accumulator, warp8 = TMA producer, warp9 = MMA issuer, warp10 = TMEM allocator, warp11 = barrier init.
+// The issuing warps deliberately have the HIGHEST warp ids: the SM's issue arbiter favours higher warp ids, and a
+// math-heavy epilogue (GELU) on low ids otherwise starves the single-thread MMA / TMA issuers.
 #include "common.cuh"
 #include "../../include/pixparse_b200.h"
 
@@ -65,6 +67,126 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_t
   n_tile = r / gsize;
 }
 
+// Phase 2 of the epilogue for one 128 x 32 staging tile: each thread owns 4 consecutive columns of 8 rows
+// (rows 16 apart), reads them back from the swizzled staging tile and applies the fused epilogue with
+// coalesced global accesses. INTERIOR = the whole 128 x BN tile is inside the matrix (no predicates at all).
+// Auxiliary operand of the fused epilogue (fp32 residual / bf16 GELU pre-activation) for the 8 rows a thread owns.
+// Issued at the top of a chunk so that the global-load latency hides under the TMEM load, staging and barriers.
+struct EpiAux {
+  float4 f[8];
+  uint2 h[8];
+};
+template <int EPI>
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, int row0, int col, EpiAux& aux) {
+  if (col + 3 >= p.N) return;      // partial column group: handled element-wise in epilogue_rows
+  if (EPI == B200_EPI_RESID_F32) {
+    const float* a = reinterpret_cast<const float*>(p.aux) + (long long)row0 * p.ld_aux + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (row0 + 16 * i < p.M) aux.f[i] = *reinterpret_cast<const float4*>(a);
+      a += 16 * p.ld_aux;
+    }
+  }
+  if (EPI == B200_EPI_DGELU_BF16) {
+    const bf16* a = reinterpret_cast<const bf16*>(p.aux) + (long long)row0 * p.ld_aux + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (row0 + 16 * i < p.M) aux.h[i] = *reinterpret_cast<const uint2*>(a);
+      a += 16 * p.ld_aux;
+    }
+  }
+}
+
+template <int EPI, bool INTERIOR>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t* buf, int et, int row0, int col,
+                                              const EpiAux& aux) {
+  const int cq = et & 7;
+  const int rt0 = et >> 3;
+  if (!INTERIOR && col >= p.N) return;
+  const bool full4 = INTERIOR || (col + 3 < p.N);
+  float b4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias != nullptr) {
+    if (full4) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
+    } else {
+      for (int e = 0; e < 4; ++e)
+        if (col + e < p.N) b4[e] = __ldg(p.bias + col + e);
+    }
+  }
+  const long long out_off = (long long)row0 * p.ldo + col;
+  const long long out_step = 16 * p.ldo;
+  bf16* o16 = reinterpret_cast<bf16*>(p.out) + out_off;
+  float* o32 = reinterpret_cast<float*>(p.out) + out_off;
+  bf16* o2 = (EPI == B200_EPI_GELU_BF16) ? reinterpret_cast<bf16*>(p.out2) + (long long)row0 * p.ldo2 + col : nullptr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rt = rt0 + 16 * i;
+    if (INTERIOR || row0 + 16 * i < p.M) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
+      float v[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1], __uint_as_float(raw.z) + b4[2],
+                    __uint_as_float(raw.w) + b4[3]};
+      if (EPI == B200_EPI_STORE_BF16) {
+        if (full4) {
+          *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+        } else {
+          for (int e = 0; e < 4; ++e)
+            if (col + e < p.N) o16[e] = __float2bfloat16_rn(v[e]);
+        }
+      } else if (EPI == B200_EPI_GELU_BF16) {
+        // out2 = pre-activation h (bf16); out = gelu(h) evaluated on the ROUNDED h (what autocast feeds nn.GELU)
+        const uint32_t h01 = pack_bf16(v[0], v[1]), h23 = pack_bf16(v[2], v[3]);
+        const float g0 = gelu_erf(bf16_lo(h01)), g1 = gelu_erf(bf16_hi(h01));
+        const float g2 = gelu_erf(bf16_lo(h23)), g3 = gelu_erf(bf16_hi(h23));
+        if (full4) {
+          *reinterpret_cast<uint2*>(o2) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, g3));
+        } else {
+          const float hv[4] = {bf16_lo(h01), bf16_hi(h01), bf16_lo(h23), bf16_hi(h23)};
+          const float gv[4] = {g0, g1, g2, g3};
+          for (int e = 0; e < 4; ++e)
+            if (col + e < p.N) {
+              o2[e] = __float2bfloat16_rn(hv[e]);
+              o16[e] = __float2bfloat16_rn(gv[e]);
+            }
+        }
+      } else if (EPI == B200_EPI_RESID_F32) {
+        // out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
+        if (full4) {
+          const float4 rv = aux.f[i];
+          *reinterpret_cast<float4*>(o32) = make_float4(rv.x + v[0], rv.y + v[1], rv.z + v[2], rv.w + v[3]);
+        } else {
+          const float* a = reinterpret_cast<const float*>(p.aux) + (long long)(row0 + 16 * i) * p.ld_aux + col;
+          for (int e = 0; e < 4; ++e)
+            if (col + e < p.N) o32[e] = a[e] + v[e];
+        }
+      } else if (EPI == B200_EPI_DGELU_BF16) {
+        // out = acc * gelu'(h), h = saved bf16 pre-activation
+        if (full4) {
+          const uint2 hv = aux.h[i];
+          *reinterpret_cast<uint2*>(o16) =
+              make_uint2(pack_bf16(v[0] * gelu_erf_grad(bf16_lo(hv.x)), v[1] * gelu_erf_grad(bf16_hi(hv.x))),
+                         pack_bf16(v[2] * gelu_erf_grad(bf16_lo(hv.y)), v[3] * gelu_erf_grad(bf16_hi(hv.y))));
+        } else {
+          const bf16* a = reinterpret_cast<const bf16*>(p.aux) + (long long)(row0 + 16 * i) * p.ld_aux + col;
+          for (int e = 0; e < 4; ++e)
+            if (col + e < p.N) o16[e] = __float2bfloat16_rn(v[e] * gelu_erf_grad(__bfloat162float(a[e])));
+        }
+      } else if (EPI == B200_EPI_STORE_F32) {
+        if (full4) {
+          *reinterpret_cast<float4*>(o32) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          for (int e = 0; e < 4; ++e)
+            if (col + e < p.N) o32[e] = v[e];
+        }
+      }
+    }
+    o16 += out_step;
+    o32 += out_step;
+    if (EPI == B200_EPI_GELU_BF16) o2 += 16 * p.ldo2;
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -85,12 +207,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (EPI == B200_EPI_REDUCE_F32) prefetch_tmap(&tmap_out);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 11 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -101,7 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 10) {
     tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tmem_relinquish();
   }
@@ -112,9 +234,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loop and one elected lane issues: TMA / tcgen05 instructions take
+    // uniform registers, and under a divergent `if (lane == 0)` the compiler wraps each of them in a
+    // per-lane serialisation loop (measured: ~200 cycles per tcgen05.mma instead of 172).
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -124,23 +249,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (!A_MN) {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
-          } else {
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m_tile * BM + j * 64, kb * BK);
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
-          } else {
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m_tile * BM + j * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n_tile * BN + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n_tile * BN + j * 64, kb * BK);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -148,9 +276,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 9) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -171,28 +299,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t da = make_smem_desc(sa, p.a_lbo, p.a_sbo);
           const uint64_t db = make_smem_desc(sb, p.b_lbo, p.b_sbo);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_ss(tmem_d, da + (uint64_t)(k * p.a_kadv), db + (uint64_t)(k * p.b_kadv), idesc,
-                    (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_ss(tmem_d, da + (uint64_t)(k * p.a_kadv), db + (uint64_t)(k * p.b_kadv), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ===================== epilogue (2 groups x 128 threads) =====================
-    const int grp = (warp - 4) >> 2;           // chunk parity handled by this group
-    const int et = (threadIdx.x - 128) & 127;  // thread index inside the group
+    const int grp = warp >> 2;                 // chunk parity handled by this group
+    const int et = threadIdx.x & 127;          // thread index inside the group
     const int ew = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
     const int row_in_tile = ew * 32 + lane;    // accumulator row owned in phase 1
     const uint32_t bar_id = 1 + grp;
@@ -205,10 +336,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const bool interior = (m_tile * BM + BM <= p.M) && (n_tile * BN + BN <= p.N);   // warp-uniform
+      const int row0 = m_tile * BM + (et >> 3);
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + grp * EPI_COLS, r);     // first chunk of this group; later chunks are prefetched below
 #pragma unroll 1
       for (int c = grp; c < BN / EPI_COLS; c += 2) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * EPI_COLS, r);
+        const int col = n_tile * BN + c * EPI_COLS + (et & 7) * 4;
+        EpiAux aux;
+        if (EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_DGELU_BF16) epilogue_prefetch<EPI>(p, row0, col, aux);
         tmem_ld_wait();
         if (c + 2 >= BN / EPI_COLS) {
           // this thread's last TMEM read of the accumulator stage: hand it back to the MMA warp
@@ -230,6 +366,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = v;
           }
         }
+        // r is dead: start the TMEM load of this group's next chunk so it overlaps the barrier + phase 2
+        if (c + 2 < BN / EPI_COLS) tmem_ld_32x32(taddr + (c + 2) * EPI_COLS, r);
         if (EPI == B200_EPI_REDUCE_F32) {
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
@@ -240,110 +378,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         } else {
           named_bar_sync(bar_id, 128);
           // phase 2: coalesced pass. thread -> (row = et/8 + 16*i, 4 columns at (et%8)*4)
-          const int cq = et & 7;
-          const int col = n_tile * BN + c * EPI_COLS + cq * 4;
-          const int row0 = m_tile * BM + (et >> 3);
-          float b4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (col + e < p.N) b4[e] = __ldg(p.bias + col + e);
-          }
-          const bool full4 = (col + 3 < p.N);
-          if (col < p.N) {
-            // batch the auxiliary loads so that 8 requests per thread are in flight
-            float4 auxf[8];
-            uint2 auxh[8];
-            if (EPI == B200_EPI_RESID_F32 && full4) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int row = row0 + 16 * i;
-                if (row < p.M)
-                  auxf[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) +
-                                                             (long long)row * p.ld_aux + col);
-              }
-            }
-            if (EPI == B200_EPI_DGELU_BF16 && full4) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int row = row0 + 16 * i;
-                if (row < p.M)
-                  auxh[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.aux) +
-                                                            (long long)row * p.ld_aux + col);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rt = (et >> 3) + 16 * i;
-              const int row = row0 + 16 * i;
-              if (row >= p.M) continue;
-              const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
-              float v[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1],
-                            __uint_as_float(raw.z) + b4[2], __uint_as_float(raw.w) + b4[3]};
-              if (EPI == B200_EPI_STORE_BF16) {
-                bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
-                if (full4) {
-                  *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e]);
-                }
-              } else if (EPI == B200_EPI_GELU_BF16) {
-                // out2 = pre-activation h (bf16), out = gelu(h) computed from the rounded h (matches autocast)
-                bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
-                bf16* o2 = reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col;
-                float g[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[e] = round_bf16(v[e]);
-                  g[e] = gelu_erf(v[e]);
-                }
-                if (full4) {
-                  *reinterpret_cast<uint2*>(o2) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                  *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (col + e < p.N) {
-                      o2[e] = __float2bfloat16_rn(v[e]);
-                      o[e] = __float2bfloat16_rn(g[e]);
-                    }
-                }
-              } else if (EPI == B200_EPI_RESID_F32) {
-                // out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
-                float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-                if (full4) {
-                  const float4 rv = auxf[i];
-                  *reinterpret_cast<float4*>(o) = make_float4(rv.x + v[0], rv.y + v[1], rv.z + v[2], rv.w + v[3]);
-                } else {
-                  const float* a = reinterpret_cast<const float*>(p.aux) + (long long)row * p.ld_aux + col;
-                  for (int e = 0; e < 4; ++e)
-                    if (col + e < p.N) o[e] = a[e] + v[e];
-                }
-              } else if (EPI == B200_EPI_DGELU_BF16) {
-                // out = acc * gelu'(h), h = saved bf16 pre-activation
-                bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col;
-                if (full4) {
-                  const uint2 hv = auxh[i];
-                  const float h0 = bf16_lo(hv.x), h1 = bf16_hi(hv.x), h2 = bf16_lo(hv.y), h3 = bf16_hi(hv.y);
-                  *reinterpret_cast<uint2*>(o) =
-                      make_uint2(pack_bf16(v[0] * gelu_erf_grad(h0), v[1] * gelu_erf_grad(h1)),
-                                 pack_bf16(v[2] * gelu_erf_grad(h2), v[3] * gelu_erf_grad(h3)));
-                } else {
-                  const bf16* a = reinterpret_cast<const bf16*>(p.aux) + (long long)row * p.ld_aux + col;
-                  for (int e = 0; e < 4; ++e)
-                    if (col + e < p.N) o[e] = __float2bfloat16_rn(v[e] * gelu_erf_grad(__bfloat162float(a[e])));
-                }
-              } else if (EPI == B200_EPI_STORE_F32) {
-                float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-                if (full4) {
-                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-                  for (int e = 0; e < 4; ++e)
-                    if (col + e < p.N) o[e] = v[e];
-                }
-              }
-            }
-          }
+          if (interior) epilogue_rows<EPI, true>(p, buf, et, row0, col, aux);
+          else epilogue_rows<EPI, false>(p, buf, et, row0, col, aux);
         }
       }
       if (++acc == 2) {
@@ -358,7 +394,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (warp == 10) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,6 +16,15 @@ def bwd():
     ops.attention_bwd(qkv, qkv, qkv, out, dout, lse, dqkv, dqkv, dqkv, B=B, H=H, Sq=S, Sk=S, q_col0=0, k_col0=D,
                       v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D)
 iters = int(os.environ.get("ITERS", "10"))
+from pixparse_b200 import _lib
+def timeit(fn):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 for name, fn, flops in (("fwd", fwd, 4.0 * B * H * S * S * 64), ("bwd", bwd, 10.0 * B * H * S * S * 64)):
     for _ in range(2): fn()
     torch.cuda.synchronize()
