@@ -157,6 +157,8 @@ def run_b200_arm(args):
     torch.manual_seed(0)
     task = TaskCrullerPretrain(cfg, env, monitor=None, tokenizer=synthetic.SyntheticBartTokenizer())
     assert task.vocab_size == synthetic.PRETRAIN_VOCAB
+    if args.dropout_off:
+        task.model.text_decoder.trunk.set_dropout(0.0)
     task.train_setup(num_batches_per_interval=1000)
     task.train_interval_start()
     B = args.batch
@@ -256,7 +258,11 @@ def run_b200_arm(args):
                                f"{B} synthetic 576x448 grayscale pages + 512-token targets per GPU",
                    "global_batch": world * B, "seq_len": 512, "parallelism": f"dp{world}",
                    "l2": "working set (activations >> 126 MB) is larger than L2; 4 distinct batches rotate",
-                   "dropout": 0.0, "gflop_per_page": GFLOP_PER_PAGE},
+                   "dropout": {"decoder": task.model.text_decoder.trunk.config.dropout,
+                               "attention": task.model.text_decoder.trunk.config.attention_dropout,
+                               "activation": task.model.text_decoder.trunk.config.activation_dropout,
+                               "encoder": 0.0, "note": "live in train_step as in the reference (bart-base config)"},
+                   "gflop_per_page": GFLOP_PER_PAGE},
         "mfu": {"vs_measured_burst": mfu_burst,
                 "vs_measured_sustained": pages_per_s * GFLOP_PER_PAGE / 1e3 / (world * peaks["bf16_sustained"]),
                 "vs_nominal_2250": pages_per_s * GFLOP_PER_PAGE / 1e3 / (world * 2250.0)},
@@ -289,6 +295,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="pages per GPU (BASELINE config: 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout-off", action="store_true", help="diagnostic only: the reference trains with dropout 0.1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

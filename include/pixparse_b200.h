@@ -118,6 +118,41 @@ int b200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_
                     const void* segments, int num_segments, const float* norm_stats, float grad_scale, float lr,
                     float beta1, float beta2, float eps, int step, int zero_grad, void* stream);
 
+/* ---- dropout-fused variants ------------------------------------------------------------------------
+ * BART trains with dropout live (bart-base: dropout = attention_dropout = activation_dropout = 0.1; the reference
+ * never calls model.eval() in train_step). Masks are stateless: keep(seed, element index) from a
+ * counter-based hash, regenerated identically in backward; kept values are scaled by 1 / (1 - p).
+ *   gemm:      RESID_F32  out = aux + drop(acc + bias)      (BartDecoderLayer: dropout before each residual add)
+ *              GELU_BF16  out = drop(gelu(h)), out2 = h      (activation_dropout)
+ *              DGELU_BF16 out = mask * acc * gelu'(aux)       (its backward)
+ *   layernorm: fwd drops the normalised OUTPUT (dropout(layernorm_embedding(x)));
+ *              bwd: in_*  = that output mask applied to the incoming gradient,
+ *                   out_* = mask of the sub-layer output feeding this LayerNorm, applied to dx_bf16 only
+ *   attention: dropout on the softmax probabilities (normaliser computed before dropping, as F.dropout(softmax))
+ */
+int b200_gemm_bf16_dropout(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                           int M, int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
+                           const float* bias, const void* aux, long long ld_aux, int splits, int block_n,
+                           float drop_p, unsigned int drop_seed, void* stream);
+int b200_layernorm_fwd_dropout(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                               float* mean, float* rstd, int rows, int dim, float eps, float drop_p,
+                               unsigned int drop_seed, void* stream);
+int b200_layernorm_bwd_dropout(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
+                               const float* mean, const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16,
+                               float* dgamma, float* dbeta, int rows, int dim, float in_p, unsigned int in_seed,
+                               float out_p, unsigned int out_seed, void* stream);
+int b200_attention_fwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                               const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
+                               int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
+                               unsigned int drop_seed, void* stream);
+int b200_attention_bwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                               const void* v, long long ldv, int v_col0, const void* o, long long ld_o,
+                               const void* d_o, long long ld_do, int do_col0, const float* lse, void* dq,
+                               long long ld_dq, int dq_col0, void* dk, long long ld_dk, int dk_col0, void* dv,
+                               long long ld_dv, int dv_col0, void* workspace, int B, int H, int Sq, int Sk,
+                               int head_dim, int causal, float scale, float drop_p, unsigned int drop_seed,
+                               void* stream);
+
 /* bring-up aid: override the UMMA shared-memory descriptor fields (-1 keeps the default) */
 int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv);
 

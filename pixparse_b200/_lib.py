@@ -42,6 +42,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _L = ctypes.c_longlong
 _F = ctypes.c_float
+_U = ctypes.c_uint
 
 # name -> argtypes; must mirror include/pixparse_b200.h exactly (tests/test_abi.py checks the symbol list)
 SIGNATURES = {
@@ -65,6 +66,12 @@ SIGNATURES = {
     "b200_grad_norm": [_P, _L, _P, _P, _F, _F, _P],
     "b200_grad_norm_workspace_floats": [],
     "b200_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _I, _P, _F, _F, _F, _F, _F, _I, _I, _P],
+    "b200_gemm_bf16_dropout": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _F, _U, _P],
+    "b200_layernorm_fwd_dropout": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _U, _P],
+    "b200_layernorm_bwd_dropout": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U, _F, _U, _P],
+    "b200_attention_fwd_dropout": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _F, _U, _P],
+    "b200_attention_bwd_dropout": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _L, _I, _P, _P, _L, _I, _P, _L, _I, _P,
+                                   _L, _I, _P, _I, _I, _I, _I, _I, _I, _F, _F, _U, _P],
     "b200_gemm_bf16": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P],
 }
 
@@ -96,7 +103,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (grad_norm: partial + final; attention_bwd: prep + main + dq convert)
-_KERNELS_PER_CALL = {"b200_grad_norm": 2, "b200_attention_bwd": 3}
+_KERNELS_PER_CALL = {"b200_grad_norm": 2, "b200_attention_bwd": 3, "b200_attention_bwd_dropout": 3}
 _launches = 0
 _profile = None     # {name: [(start_event, end_event, flops), ...]} while profile_ops() is active
 
@@ -113,15 +120,17 @@ def launch_count():
 def call(name, *args):
     global _launches
     prof = _profile
-    if prof is not None and name in prof:
+    pname = name[:-8] if name.endswith("_dropout") else name      # dropout variants are profiled with their base op
+    if prof is not None and pname in prof:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib(), name)(*args)
         e1.record()
-        flops = 2.0 * args[6] * args[7] * args[8] if name == "b200_gemm_bf16" else 0.0
-        tag = (f"gemm a_mn={args[2]} b_mn={args[5]} epi={args[9]}" if name == "b200_gemm_bf16" else name)
-        prof[name].append((e0, e1, flops, tag))
+        is_gemm = name.startswith("b200_gemm_bf16")
+        flops = 2.0 * args[6] * args[7] * args[8] if is_gemm else 0.0
+        tag = (f"gemm a_mn={args[2]} b_mn={args[5]} epi={args[9]}" if is_gemm else name)
+        prof[pname].append((e0, e1, flops, tag))
     else:
         rc = getattr(lib(), name)(*args)
     if rc != 0:

@@ -34,6 +34,7 @@ struct AttBwdParams {
   bf16* dk; long long ld_dk; int dk_col0;
   bf16* dv; long long ld_dv; int dv_col0;
   int q_col0, k_col0, v_col0, do_col0;
+  uint32_t drop_threshold16, drop_seed;   // attention-probability dropout of the forward pass (0 = off)
 };
 
 // Pipeline per query tile t (tensor pipe on the left, the 8 compute warps on the right run concurrently):
@@ -269,21 +270,41 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         uint32_t rs[32];
         tmem_ld_32x32(lane_addr + TB_S + half * 64 + c * 32, rs);
         tmem_ld_wait();
+        if (need_mask) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float v = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
-          if (need_mask && (kbase + c * 32 + e > kmax)) v = 0.f;
-          pv[c * 32 + e] = v;
+          for (int e = 0; e < 32; ++e) {
+            float v = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
+            if (kbase + c * 32 + e > kmax) v = 0.f;
+            pv[c * 32 + e] = v;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            pv[c * 32 + e] = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
         }
       }
+      // dropout pair index of (query row, key k) = drop_row + k / 2, exactly as in the forward kernel
+      const uint32_t drop_row = (uint32_t)((((long long)b * p.H + h) * p.Sq + qidx) * ((p.Sk + 1) >> 1)) +
+                                (uint32_t)(kbase >> 1);
+      const float drop_sc = dropout_scale(p.drop_threshold16);
       if (t > 0) mbar_wait(p_free, (t - 1) & 1);      // dV_{t-1} no longer reads the P buffer
       {
         uint8_t* prow = sP + half * AB_TILE + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j) {
+          float q8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) q8[e] = pv[8 * j + e];
+          if (p.drop_threshold16 != 0u) {      // dV uses the dropped probabilities
+#pragma unroll
+            for (int e = 0; e < 8; e += 2)
+              dropout_pair(p.drop_seed, drop_row + (uint32_t)((8 * j + e) >> 1), p.drop_threshold16, drop_sc, q8[e],
+                           q8[e + 1]);
+          }
           *reinterpret_cast<uint4*>(prow + ((j ^ sw) << 4)) =
-              make_uint4(pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
-                         pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
+              make_uint4(pack_bf16(q8[0], q8[1]), pack_bf16(q8[2], q8[3]), pack_bf16(q8[4], q8[5]),
+                         pack_bf16(q8[6], q8[7]));
+        }
       }
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
@@ -303,8 +324,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           tmem_ld_32x32(lane_addr + TB_DP + half * 64 + c * 32, rp);
           tmem_ld_wait();
           float dsv[32];
+          if (p.drop_threshold16 != 0u) {      // dS = P * (mask * dP - D) * scale
 #pragma unroll
-          for (int e = 0; e < 32; ++e) dsv[e] = pv[c * 32 + e] * (__uint_as_float(rp[e]) - dsum) * p.scale;
+            for (int e = 0; e < 32; e += 2) {
+              float g0 = __uint_as_float(rp[e]), g1 = __uint_as_float(rp[e + 1]);
+              dropout_pair(p.drop_seed, drop_row + (uint32_t)((c * 32 + e) >> 1), p.drop_threshold16, drop_sc, g0, g1);
+              dsv[e] = pv[c * 32 + e] * (g0 - dsum) * p.scale;
+              dsv[e + 1] = pv[c * 32 + e + 1] * (g1 - dsum) * p.scale;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dsv[e] = pv[c * 32 + e] * (__uint_as_float(rp[e]) - dsum) * p.scale;
+          }
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int piece = (c * 4 + jj) ^ sw;
@@ -409,12 +440,42 @@ extern "C" long long b200_attention_bwd_workspace_bytes(int B, int H, int Sq) {
   return ((long long)B * Sq * H * 64 + (long long)B * H * Sq) * 4;
 }
 
+static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                              const void* v, long long ldv, int v_col0, const void* o, long long ld_o, const void* d_o,
+                              long long ld_do, int do_col0, const float* lse, void* dq, long long ld_dq, int dq_col0,
+                              void* dk, long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
+                              void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
+                              float drop_p, unsigned int drop_seed, void* stream);
+
 extern "C" int b200_attention_bwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
                                   const void* v, long long ldv, int v_col0, const void* o, long long ld_o,
                                   const void* d_o, long long ld_do, int do_col0, const float* lse, void* dq,
                                   long long ld_dq, int dq_col0, void* dk, long long ld_dk, int dk_col0, void* dv,
                                   long long ld_dv, int dv_col0, void* workspace, int B, int H, int Sq, int Sk,
                                   int head_dim, int causal, float scale, void* stream) {
+  return attention_bwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, o, ld_o, d_o, ld_do, do_col0, lse, dq, ld_dq,
+                            dq_col0, dk, ld_dk, dk_col0, dv, ld_dv, dv_col0, workspace, B, H, Sq, Sk, head_dim, causal,
+                            scale, 0.f, 0u, stream);
+}
+
+extern "C" int b200_attention_bwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk,
+                                          int k_col0, const void* v, long long ldv, int v_col0, const void* o,
+                                          long long ld_o, const void* d_o, long long ld_do, int do_col0,
+                                          const float* lse, void* dq, long long ld_dq, int dq_col0, void* dk,
+                                          long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
+                                          void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal,
+                                          float scale, float drop_p, unsigned int drop_seed, void* stream) {
+  return attention_bwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, o, ld_o, d_o, ld_do, do_col0, lse, dq, ld_dq,
+                            dq_col0, dk, ld_dk, dk_col0, dv, ld_dv, dv_col0, workspace, B, H, Sq, Sk, head_dim, causal,
+                            scale, drop_p, drop_seed, stream);
+}
+
+static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                              const void* v, long long ldv, int v_col0, const void* o, long long ld_o, const void* d_o,
+                              long long ld_do, int do_col0, const float* lse, void* dq, long long ld_dq, int dq_col0,
+                              void* dk, long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
+                              void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
+                              float drop_p, unsigned int drop_seed, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(head_dim == AB_D, "b200_attention_bwd: head_dim %d unsupported (only 64)", head_dim);
   B200_CHECK_ARG(q && k && v && o && d_o && lse && dq && dk && dv && workspace, "b200_attention_bwd: null argument");
@@ -462,6 +523,9 @@ extern "C" int b200_attention_bwd(const void* q, long long ldq, int q_col0, cons
   p.dk = reinterpret_cast<bf16*>(dk); p.ld_dk = ld_dk; p.dk_col0 = dk_col0;
   p.dv = reinterpret_cast<bf16*>(dv); p.ld_dv = ld_dv; p.dv_col0 = dv_col0;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.do_col0 = do_col0;
+  B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "b200_attention_bwd: dropout p must be in [0, 1)");
+  p.drop_threshold16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
+  p.drop_seed = drop_seed;
   static bool configured = false;
   if (!configured) {
     e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);

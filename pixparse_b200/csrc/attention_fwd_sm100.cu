@@ -14,6 +14,8 @@
 //   encoder self-attention (non-causal, Sq = Sk = 1009 / 2509), decoder causal self-attention (Sq = Sk = T),
 //   decoder cross-attention over image tokens (Sq = T, Sk = S, no mask).
 // Replaces torch SDPA reached from timm Attention (fused_attn) and BartAttention (sdpa).
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/pixparse_b200.h"
 
@@ -41,6 +43,7 @@ struct AttFwdParams {
   long long ld_out;
   float* lse;              // [B, H, Sq] natural-log logsumexp of the scaled scores
   int q_col0, k_col0, v_col0;   // column offsets of head 0 inside the Q / K / V row
+  uint32_t drop_threshold16, drop_seed;   // attention-probability dropout (BART attention_dropout); 0 = off
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 4)
@@ -162,6 +165,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int qidx = q0 + row;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int causal_shift = p.Sk - p.Sq;
+    // dropout pair index of (row, key k) = drop_row + k / 2  (rows padded to an even number of keys)
+    const uint32_t drop_row = (uint32_t)((((long long)b * p.H + h) * p.Sq + qidx) * ((p.Sk + 1) >> 1));
+    const float drop_sc = dropout_scale(p.drop_threshold16);
     float m_run = -INFINITY;   // running max in the scaled log2 domain
     float l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
@@ -214,26 +220,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
       }
       // ---- pass 2: P = exp2(S * scale - m), row sum, bf16 pack -> TMEM
+      // (two instantiations: interior tiles carry no masking instructions at all)
       float l_tile = 0.f;
+      auto pass2 = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll 1
-      for (int c = 0; c < ATT_BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(lane_addr + TM_S + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(lane_addr + TM_S + c * 32, r);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_use));
-          float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_use));
-          if (need_mask) {
-            if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
-            if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
+          for (int e = 0; e < 16; ++e) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_use));
+            float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_use));
+            if (MASKED) {
+              if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
+              if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
+            }
+            l_tile += p0 + p1;        // the softmax normaliser uses the un-dropped probabilities
+            if (p.drop_threshold16 != 0u)
+              dropout_pair(p.drop_seed, drop_row + (uint32_t)((k0 + c * 32 + 2 * e) >> 1), p.drop_threshold16, drop_sc,
+                           p0, p1);
+            pk[e] = pack_bf16(p0, p1);
           }
-          l_tile += p0 + p1;
-          pk[e] = pack_bf16(p0, p1);
+          tmem_st_32x16(lane_addr + TM_P + c * 16, pk);
         }
-        tmem_st_32x16(lane_addr + TM_P + c * 16, pk);
-      }
+      };
+      if (need_mask) pass2(std::true_type{}); else pass2(std::false_type{});
       tmem_st_wait();
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
@@ -285,9 +299,31 @@ int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long widt
 
 using namespace b200;
 
+static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                              const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse, int B,
+                              int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
+                              unsigned int drop_seed, void* stream);
+
 extern "C" int b200_attention_fwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
                                   const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
                                   int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream) {
+  return attention_fwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ld_out, lse, B, H, Sq, Sk, head_dim,
+                            causal, scale, 0.f, 0u, stream);
+}
+
+extern "C" int b200_attention_fwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk,
+                                          int k_col0, const void* v, long long ldv, int v_col0, void* out,
+                                          long long ld_out, float* lse, int B, int H, int Sq, int Sk, int head_dim,
+                                          int causal, float scale, float drop_p, unsigned int drop_seed,
+                                          void* stream) {
+  return attention_fwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ld_out, lse, B, H, Sq, Sk, head_dim,
+                            causal, scale, drop_p, drop_seed, stream);
+}
+
+static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
+                              const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse, int B,
+                              int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
+                              unsigned int drop_seed, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(head_dim == ATT_D, "b200_attention_fwd: head_dim %d unsupported (only 64)", head_dim);
   B200_CHECK_ARG(q && k && v && out && B > 0 && H > 0 && Sq > 0 && Sk > 0, "b200_attention_fwd: bad arguments");
@@ -306,6 +342,9 @@ extern "C" int b200_attention_fwd(const void* q, long long ldq, int q_col0, cons
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out; p.lse = lse;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "b200_attention_fwd: dropout p must be in [0, 1)");
+  p.drop_threshold16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
+  p.drop_seed = drop_seed;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);

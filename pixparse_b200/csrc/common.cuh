@@ -321,6 +321,28 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// ---- dropout: stateless counter-based masks ---------------------------------------------------------
+// One 32-bit hash of (seed, pair index) yields two 16-bit uniforms -> keep decisions for two adjacent elements.
+// keep <=> u16 >= threshold16, threshold16 = round(p * 65536); kept values are scaled by 65536 / (65536 - threshold16).
+// Forward and backward regenerate identical masks from (seed, index); nothing is stored.
+__device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t pair_idx) {
+  uint32_t x = pair_idx * 0x9E3779B1u + seed;
+  x ^= x >> 16; x *= 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float dropout_scale(uint32_t threshold16) {
+  return 65536.0f / (65536.0f - (float)threshold16);
+}
+// multiplies the element pair (a, b) whose first element has linear index 2 * pair_idx
+__device__ __forceinline__ void dropout_pair(uint32_t seed, uint32_t pair_idx, uint32_t threshold16, float scale,
+                                             float& a, float& b) {
+  const uint32_t h = dropout_hash(seed, pair_idx);
+  a = ((h & 0xFFFFu) >= threshold16) ? a * scale : 0.f;
+  b = ((h >> 16) >= threshold16) ? b * scale : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

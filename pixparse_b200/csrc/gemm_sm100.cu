@@ -39,6 +39,9 @@ struct GemmParams {
   long long ld_aux;
   // UMMA shared-memory descriptor parameters (bytes / 16-byte units), filled by the host
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+  // dropout fused into the epilogue (threshold 0 = off): RESID drops (acc + bias) before the residual add,
+  // GELU drops the activation (not the saved pre-activation), DGELU masks the incoming gradient
+  uint32_t drop_threshold16, drop_seed;
 };
 
 // debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
@@ -126,6 +129,18 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
       const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
       float v[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1], __uint_as_float(raw.z) + b4[2],
                     __uint_as_float(raw.w) + b4[3]};
+      float dm[4] = {1.f, 1.f, 1.f, 1.f};     // dropout multipliers of the 4 columns (N is even when dropout is on)
+      if ((EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16) &&
+          p.drop_threshold16 != 0u) {
+        const uint32_t pair = (uint32_t)(((long long)(row0 + 16 * i) * p.N + col) >> 1);
+        const float sc = dropout_scale(p.drop_threshold16);
+        dropout_pair(p.drop_seed, pair, p.drop_threshold16, sc, dm[0], dm[1]);
+        dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, sc, dm[2], dm[3]);
+        if (EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_DGELU_BF16) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] *= dm[e];
+        }
+      }
       if (EPI == B200_EPI_STORE_BF16) {
         if (full4) {
           *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
@@ -136,8 +151,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
       } else if (EPI == B200_EPI_GELU_BF16) {
         // out2 = pre-activation h (bf16); out = gelu(h) evaluated on the ROUNDED h (what autocast feeds nn.GELU)
         const uint32_t h01 = pack_bf16(v[0], v[1]), h23 = pack_bf16(v[2], v[3]);
-        const float g0 = gelu_erf(bf16_lo(h01)), g1 = gelu_erf(bf16_hi(h01));
-        const float g2 = gelu_erf(bf16_lo(h23)), g3 = gelu_erf(bf16_hi(h23));
+        const float g0 = gelu_erf(bf16_lo(h01)) * dm[0], g1 = gelu_erf(bf16_hi(h01)) * dm[1];
+        const float g2 = gelu_erf(bf16_lo(h23)) * dm[2], g3 = gelu_erf(bf16_hi(h23)) * dm[3];
         if (full4) {
           *reinterpret_cast<uint2*>(o2) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, g3));
@@ -440,10 +455,32 @@ extern "C" int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo,
   return 0;
 }
 
+static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
+                     int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
+                     const float* bias, const void* aux, long long ld_aux, int splits, int block_n, float drop_p,
+                     unsigned int drop_seed, void* stream_);
+
 extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                               int b_mn_major, int M, int N, int K, int epilogue, void* out, long long ldo,
                               void* out2, long long ldo2, const float* bias, const void* aux, long long ld_aux,
                               int splits, int block_n, void* stream_) {
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, out, ldo, out2, ldo2, bias, aux, ld_aux,
+                   splits, block_n, 0.f, 0u, stream_);
+}
+
+extern "C" int b200_gemm_bf16_dropout(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                                      int b_mn_major, int M, int N, int K, int epilogue, void* out, long long ldo,
+                                      void* out2, long long ldo2, const float* bias, const void* aux,
+                                      long long ld_aux, int splits, int block_n, float drop_p,
+                                      unsigned int drop_seed, void* stream_) {
+  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, out, ldo, out2, ldo2, bias, aux, ld_aux,
+                   splits, block_n, drop_p, drop_seed, stream_);
+}
+
+static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
+                     int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
+                     const float* bias, const void* aux, long long ld_aux, int splits, int block_n, float drop_p,
+                     unsigned int drop_seed, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "b200_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   B200_CHECK_ARG(A && B && out, "b200_gemm_bf16: null operand");
@@ -489,6 +526,14 @@ extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, cons
   p.group_m = 8;
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
   p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  p.drop_threshold16 = 0; p.drop_seed = drop_seed;
+  if (drop_p > 0.f) {
+    B200_CHECK_ARG(drop_p < 1.f, "b200_gemm_bf16_dropout: p must be in [0, 1)");
+    B200_CHECK_ARG(epilogue == B200_EPI_RESID_F32 || epilogue == B200_EPI_GELU_BF16 || epilogue == B200_EPI_DGELU_BF16,
+                   "b200_gemm_bf16_dropout: dropout is fused only into the RESID / GELU / DGELU epilogues");
+    B200_CHECK_ARG(N % 4 == 0, "b200_gemm_bf16_dropout: N must be a multiple of 4");
+    p.drop_threshold16 = (uint32_t)(drop_p * 65536.0f + 0.5f);
+  }
   // K-major: rows of 128 B, 8-row groups 1024 B apart, K advance 32 B per UMMA.
   // MN-major: k-rows of 128 B (64 M/N elements), 8-k groups 1024 B apart (SBO), 64-element M/N chunks
   //           BK*128 B apart (LBO), K advance 16 rows * 128 B per UMMA.

@@ -15,7 +15,7 @@ template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      bf16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean_out,
-                     float* __restrict__ rstd_out, int rows, float eps) {
+                     float* __restrict__ rstd_out, int rows, float eps, uint32_t drop_thr, uint32_t drop_seed) {
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
@@ -51,6 +51,12 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
     o.z = (v[i].z - mean) * rstd * g.z + b.z;
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (drop_thr != 0u) {      // dropout on the normalised output (BART: dropout(layernorm_embedding(...)))
+      const uint32_t pair = (uint32_t)(((size_t)row * D + (size_t)(lane + 32 * i) * 4) >> 1);
+      const float sc = dropout_scale(drop_thr);
+      dropout_pair(drop_seed, pair, drop_thr, sc, o.x, o.y);
+      dropout_pair(drop_seed, pair + 1, drop_thr, sc, o.z, o.w);
+    }
     if (y32) reinterpret_cast<float4*>(y32 + (size_t)row * D)[lane + 32 * i] = o;
     if (y16)
       reinterpret_cast<uint2*>(y16 + (size_t)row * D)[lane + 32 * i] =
@@ -65,7 +71,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ dres32,
                      const float* __restrict__ x, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, const float* __restrict__ gamma, float* __restrict__ dx32,
-                     bf16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
+                     bf16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
+                     uint32_t in_thr, uint32_t in_seed, uint32_t out_thr, uint32_t out_seed) {
   constexpr int D = NV * 128;
   __shared__ float red[LN_WARPS][D];
   const int lane = threadIdx.x & 31;
@@ -97,6 +104,12 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy
         const float4 r = reinterpret_cast<const float4*>(dy32 + (size_t)row * D)[lane + 32 * i];
         d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w;
       }
+      if (in_thr != 0u) {      // the forward dropped this LayerNorm's OUTPUT: mask the incoming gradient the same way
+        const uint32_t pair = (uint32_t)(((size_t)row * D + (size_t)(lane + 32 * i) * 4) >> 1);
+        const float sc = dropout_scale(in_thr);
+        dropout_pair(in_seed, pair, in_thr, sc, d.x, d.y);
+        dropout_pair(in_seed, pair + 1, in_thr, sc, d.z, d.w);
+      }
       xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
       dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
       db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
@@ -118,9 +131,16 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       if (dx32) reinterpret_cast<float4*>(dx32 + (size_t)row * D)[lane + 32 * i] = o;
-      if (dx16)
+      if (dx16) {
+        if (out_thr != 0u) {   // dx16 feeds the sub-layer whose output was dropped before the residual add
+          const uint32_t pair = (uint32_t)(((size_t)row * D + (size_t)(lane + 32 * i) * 4) >> 1);
+          const float sc = dropout_scale(out_thr);
+          dropout_pair(out_seed, pair, out_thr, sc, o.x, o.y);
+          dropout_pair(out_seed, pair + 1, out_thr, sc, o.z, o.w);
+        }
         reinterpret_cast<uint2*>(dx16 + (size_t)row * D)[lane + 32 * i] =
             make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
     }
   }
   // block reduction of the parameter gradients, then one atomic per column per block
@@ -143,9 +163,9 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy
 
 template <int NV>
 static int ln_fwd_launch(const float* x, const float* gamma, const float* beta, bf16* y16, float* y32, float* mean,
-                         float* rstd, int rows, float eps, cudaStream_t s) {
+                         float* rstd, int rows, float eps, uint32_t thr, uint32_t seed, cudaStream_t s) {
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  layernorm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y32, mean, rstd, rows, eps);
+  layernorm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y32, mean, rstd, rows, eps, thr, seed);
   B200_CHECK_LAUNCH("layernorm_fwd");
   return 0;
 }
@@ -153,12 +173,13 @@ static int ln_fwd_launch(const float* x, const float* gamma, const float* beta, 
 template <int NV>
 static int ln_bwd_launch(const bf16* dy16, const float* dy32, const float* dres32, const float* x, const float* mean,
                          const float* rstd, const float* gamma, float* dx32, bf16* dx16, float* dgamma, float* dbeta,
-                         int rows, cudaStream_t s) {
+                         int rows, uint32_t in_thr, uint32_t in_seed, uint32_t out_thr, uint32_t out_seed,
+                         cudaStream_t s) {
   int grid = num_sms() * 4;
   const int need = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > need) grid = need;
   layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy32, dres32, x, mean, rstd, gamma, dx32, dx16,
-                                                          dgamma, dbeta, rows);
+                                                          dgamma, dbeta, rows, in_thr, in_seed, out_thr, out_seed);
   B200_CHECK_LAUNCH("layernorm_bwd");
   return 0;
 }
@@ -167,37 +188,71 @@ static int ln_bwd_launch(const bf16* dy16, const float* dy32, const float* dres3
 
 using namespace b200;
 
-extern "C" int b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
-                                  float* mean, float* rstd, int rows, int dim, float eps, void* stream) {
+static inline uint32_t thr16(float p) { return p > 0.f ? (uint32_t)(p * 65536.0f + 0.5f) : 0u; }
+
+static int ln_fwd_dispatch(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                           float* mean, float* rstd, int rows, int dim, float eps, float drop_p, unsigned int drop_seed,
+                           void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(rows > 0 && x && gamma && beta, "b200_layernorm_fwd: bad arguments");
+  B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "b200_layernorm_fwd: dropout p must be in [0, 1)");
   bf16* y16 = reinterpret_cast<bf16*>(y_bf16);
+  const uint32_t t = thr16(drop_p);
   switch (dim) {
-    case 128: return ln_fwd_launch<1>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, s);
-    case 256: return ln_fwd_launch<2>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, s);
-    case 512: return ln_fwd_launch<4>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, s);
-    case 768: return ln_fwd_launch<6>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, s);
-    case 1024: return ln_fwd_launch<8>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, s);
+    case 128: return ln_fwd_launch<1>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, t, drop_seed, s);
+    case 256: return ln_fwd_launch<2>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, t, drop_seed, s);
+    case 512: return ln_fwd_launch<4>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, t, drop_seed, s);
+    case 768: return ln_fwd_launch<6>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, t, drop_seed, s);
+    case 1024: return ln_fwd_launch<8>(x, gamma, beta, y16, y_f32, mean, rstd, rows, eps, t, drop_seed, s);
   }
   set_last_error("b200_layernorm_fwd: unsupported dim %d (supported: 128, 256, 512, 768, 1024)", dim);
   return -1;
 }
 
-extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
-                                  const float* mean, const float* rstd, const float* gamma, float* dx_f32,
-                                  void* dx_bf16, float* dgamma, float* dbeta, int rows, int dim, void* stream) {
+static int ln_bwd_dispatch(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
+                           const float* mean, const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16,
+                           float* dgamma, float* dbeta, int rows, int dim, float in_p, unsigned int in_seed,
+                           float out_p, unsigned int out_seed, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(rows > 0 && x && mean && rstd && gamma && dgamma && dbeta, "b200_layernorm_bwd: bad arguments");
   B200_CHECK_ARG(dy_bf16 || dy_f32, "b200_layernorm_bwd: need dy_bf16 and/or dy_f32");
   const bf16* dy16 = reinterpret_cast<const bf16*>(dy_bf16);
   bf16* dx16 = reinterpret_cast<bf16*>(dx_bf16);
+  const uint32_t ti = thr16(in_p), to = thr16(out_p);
   switch (dim) {
-    case 128: return ln_bwd_launch<1>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, s);
-    case 256: return ln_bwd_launch<2>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, s);
-    case 512: return ln_bwd_launch<4>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, s);
-    case 768: return ln_bwd_launch<6>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, s);
-    case 1024: return ln_bwd_launch<8>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, s);
+    case 128: return ln_bwd_launch<1>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, ti, in_seed, to, out_seed, s);
+    case 256: return ln_bwd_launch<2>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, ti, in_seed, to, out_seed, s);
+    case 512: return ln_bwd_launch<4>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, ti, in_seed, to, out_seed, s);
+    case 768: return ln_bwd_launch<6>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, ti, in_seed, to, out_seed, s);
+    case 1024: return ln_bwd_launch<8>(dy16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx16, dgamma, dbeta, rows, ti, in_seed, to, out_seed, s);
   }
   set_last_error("b200_layernorm_bwd: unsupported dim %d (supported: 128, 256, 512, 768, 1024)", dim);
   return -1;
+}
+
+extern "C" int b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                                  float* mean, float* rstd, int rows, int dim, float eps, void* stream) {
+  return ln_fwd_dispatch(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, 0.f, 0u, stream);
+}
+
+extern "C" int b200_layernorm_fwd_dropout(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                                          float* y_f32, float* mean, float* rstd, int rows, int dim, float eps,
+                                          float drop_p, unsigned int drop_seed, void* stream) {
+  return ln_fwd_dispatch(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, drop_p, drop_seed, stream);
+}
+
+extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
+                                  const float* mean, const float* rstd, const float* gamma, float* dx_f32,
+                                  void* dx_bf16, float* dgamma, float* dbeta, int rows, int dim, void* stream) {
+  return ln_bwd_dispatch(dy_bf16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx_bf16, dgamma, dbeta, rows, dim,
+                         0.f, 0u, 0.f, 0u, stream);
+}
+
+extern "C" int b200_layernorm_bwd_dropout(const void* dy_bf16, const float* dy_f32, const float* dres_f32,
+                                          const float* x, const float* mean, const float* rstd, const float* gamma,
+                                          float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int rows, int dim,
+                                          float in_p, unsigned int in_seed, float out_p, unsigned int out_seed,
+                                          void* stream) {
+  return ln_bwd_dispatch(dy_bf16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx_bf16, dgamma, dbeta, rows, dim,
+                         in_p, in_seed, out_p, out_seed, stream);
 }

@@ -123,9 +123,12 @@ class CrullerEngine:
             self.bart.__dict__['_b200_engine_ref'] = weakref.ref(self)
         self.arena = None
         self.saved = None
-        self.dropout_p = 0.0
         self._shadow_fresh = False
         self._param_versions = None
+        # dropout: live in training mode exactly where BartDecoder applies it (the ViT has all drop rates 0);
+        # masks are regenerated from (seed, site) in backward, the seed advances every forward
+        self.dropout_seed = 0x5EED
+        self._dropout_calls = 0
 
     # ------------------------------------------------------------------------------------------------ binding
     def invalidate(self):
@@ -316,6 +319,27 @@ class CrullerEngine:
             ops.colsum(dproj, ar.grad("vit.patch.b"))
 
     # ------------------------------------------------------------------------------------------------ decoder
+    class _Drop:
+        """(p, seed) pairs for every dropout site of one decoder forward/backward."""
+
+        def __init__(self, cfg, base_seed, training):
+            on = bool(training)
+            self.p = float(cfg.dropout) if on else 0.0
+            self.pa = float(cfg.attention_dropout) if on else 0.0
+            self.pact = float(cfg.activation_dropout) if on else 0.0
+            self.base = int(base_seed) & 0xFFFFFFFF
+
+        def _seed(self, site):
+            return (self.base * 2654435761 + site * 40503 + 12345) & 0xFFFFFFFF
+
+        def emb(self):
+            return (self.p, self._seed(0))
+
+        def site(self, layer, k):
+            # k: 0 self-attn probs, 1 self-attn out, 2 cross-attn probs, 3 cross-attn out, 4 activation, 5 ffn out
+            p = (self.pa, self.p, self.pa, self.p, self.pact, self.p)[k]
+            return (p, self._seed(1 + 8 * layer + k))
+
     def decoder_forward(self, ids, enc16, B, S, save):
         ar, bart = self.arena, self.bart
         cfg = bart.config
@@ -330,8 +354,12 @@ class CrullerEngine:
             ids = ids.long().contiguous()
         st = _Saved()
         st.B, st.T, st.S, st.V, st.ids = B, T, S, V, ids
+        self._dropout_calls += 1
+        dr = CrullerEngine._Drop(cfg, self.dropout_seed + 7919 * self._dropout_calls, save and bart.training)
+        st.drop = dr
         x_emb = ops.embed_fwd(ids, ar.w32("dec.tok"), ar.w32("dec.pos"), pos_offset=2, scale=1.0)
-        h16, h32, me, re_ = ops.layernorm_fwd(x_emb, ar.w32("dec.ln_emb.w"), ar.w32("dec.ln_emb.b"), eps, want_f32=True)
+        h16, h32, me, re_ = ops.layernorm_fwd(x_emb, ar.w32("dec.ln_emb.w"), ar.w32("dec.ln_emb.b"), eps, want_f32=True,
+                                              drop=dr.emb())
         st.emb = (x_emb, me, re_)
         st.layers = []
         for j in range(nl):
@@ -341,9 +369,10 @@ class CrullerEngine:
             bqkv = ar.span(k + "sa.q.b", k + "sa.v.b", "w32")
             qkv = ops.gemm(h16, wqkv, bias=bqkv)
             a_s, lse_s = ops.attention_fwd(qkv, qkv, qkv, B=B, H=Hh, Sq=T, Sk=T, q_col0=0, k_col0=D, v_col0=2 * D,
-                                           causal=True)
+                                           causal=True, drop=dr.site(j, 0))
             u1 = torch.empty_like(h32)
-            ops.gemm(a_s, ar.w16(k + "sa.o.w"), bias=ar.w32(k + "sa.o.b"), epi=EPI_RESID_F32, aux=h32, out=u1)
+            ops.gemm(a_s, ar.w16(k + "sa.o.w"), bias=ar.w32(k + "sa.o.b"), epi=EPI_RESID_F32, aux=h32, out=u1,
+                     drop=dr.site(j, 1))
             h1_16, h1_32, m1, r1 = ops.layernorm_fwd(u1, ar.w32(k + "sa_ln.w"), ar.w32(k + "sa_ln.b"), eps,
                                                      want_f32=True)
             # cross-attention over the image tokens (k|v packed)
@@ -351,17 +380,21 @@ class CrullerEngine:
             wkv = ar.span(k + "ca.k.w", k + "ca.v.w", "w16").view(2 * D, D)
             bkv = ar.span(k + "ca.k.b", k + "ca.v.b", "w32")
             kvc = ops.gemm(enc16, wkv, bias=bkv)
-            a_c, lse_c = ops.attention_fwd(qc, kvc, kvc, B=B, H=Hh, Sq=T, Sk=S, q_col0=0, k_col0=0, v_col0=D)
+            a_c, lse_c = ops.attention_fwd(qc, kvc, kvc, B=B, H=Hh, Sq=T, Sk=S, q_col0=0, k_col0=0, v_col0=D,
+                                           drop=dr.site(j, 2))
             u2 = torch.empty_like(h32)
-            ops.gemm(a_c, ar.w16(k + "ca.o.w"), bias=ar.w32(k + "ca.o.b"), epi=EPI_RESID_F32, aux=h1_32, out=u2)
+            ops.gemm(a_c, ar.w16(k + "ca.o.w"), bias=ar.w32(k + "ca.o.b"), epi=EPI_RESID_F32, aux=h1_32, out=u2,
+                     drop=dr.site(j, 3))
             h2_16, h2_32, m2, r2 = ops.layernorm_fwd(u2, ar.w32(k + "ca_ln.w"), ar.w32(k + "ca_ln.b"), eps,
                                                      want_f32=True)
             # feed-forward
             F_ = ar.index[k + "fc1.w"][2][0]
             hpre = torch.empty((M, F_), device=h16.device, dtype=torch.bfloat16)
-            g = ops.gemm(h2_16, ar.w16(k + "fc1.w"), bias=ar.w32(k + "fc1.b"), epi=EPI_GELU_BF16, out2=hpre)
+            g = ops.gemm(h2_16, ar.w16(k + "fc1.w"), bias=ar.w32(k + "fc1.b"), epi=EPI_GELU_BF16, out2=hpre,
+                         drop=dr.site(j, 4))
             u3 = torch.empty_like(h32)
-            ops.gemm(g, ar.w16(k + "fc2.w"), bias=ar.w32(k + "fc2.b"), epi=EPI_RESID_F32, aux=h2_32, out=u3)
+            ops.gemm(g, ar.w16(k + "fc2.w"), bias=ar.w32(k + "fc2.b"), epi=EPI_RESID_F32, aux=h2_32, out=u3,
+                     drop=dr.site(j, 5))
             h3_16, h3_32, m3, r3 = ops.layernorm_fwd(u3, ar.w32(k + "f_ln.w"), ar.w32(k + "f_ln.b"), eps,
                                                      want_f32=True)
             if save:
@@ -382,6 +415,7 @@ class CrullerEngine:
         D, Hh, nl = cfg.d_model, cfg.decoder_attention_heads, cfg.decoder_layers
         B, T, S, V = st.B, st.T, st.S, st.V
         enc16 = st.enc16
+        dr = st.drop
         # lm_head (tied to embed_tokens): dgrad + wgrad
         dy16 = ops.gemm(dlogits, ar.w16("dec.tok"), b_mn=True, K=V)
         ops.gemm(dlogits, st.h_last16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad("dec.tok"), M=V)
@@ -392,9 +426,10 @@ class CrullerEngine:
             (h0_16, qkv, a_s, lse_s, u1, m1, r1, h1_16, qc, kvc, a_c, lse_c, u2, m2, r2, h2_16, hpre, g, u3, m3,
              r3) = st.layers[j]
             # final LN (post-LN): du3 = LNbwd(dy)
+            # du16 carries the mask of the sub-layer output that was dropped before the residual add (du32 does not)
             du32, du16 = ops.layernorm_bwd(u3, m3, r3, ar.w32(k + "f_ln.w"), ar.grad(k + "f_ln.w"),
-                                           ar.grad(k + "f_ln.b"), dy16=dy16, dy32=dy32)
-            d_h = ops.gemm(du16, ar.w16(k + "fc2.w"), b_mn=True, epi=EPI_DGELU_BF16, aux=hpre)
+                                           ar.grad(k + "f_ln.b"), dy16=dy16, dy32=dy32, out_drop=dr.site(j, 5))
+            d_h = ops.gemm(du16, ar.w16(k + "fc2.w"), b_mn=True, epi=EPI_DGELU_BF16, aux=hpre, drop=dr.site(j, 4))
             ops.gemm(du16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"))
             ops.colsum(du16, ar.grad(k + "fc2.b"))
             d_h2 = ops.gemm(d_h, ar.w16(k + "fc1.w"), b_mn=True)
@@ -402,14 +437,15 @@ class CrullerEngine:
             ops.colsum(d_h, ar.grad(k + "fc1.b"))
             # cross-attention LN
             du32, du16 = ops.layernorm_bwd(u2, m2, r2, ar.w32(k + "ca_ln.w"), ar.grad(k + "ca_ln.w"),
-                                           ar.grad(k + "ca_ln.b"), dy16=d_h2, dy32=du32, dx32=du32, dx16=du16)
+                                           ar.grad(k + "ca_ln.b"), dy16=d_h2, dy32=du32, dx32=du32, dx16=du16,
+                                           out_drop=dr.site(j, 3))
             d_ac = ops.gemm(du16, ar.w16(k + "ca.o.w"), b_mn=True)
             ops.gemm(du16, a_c, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.o.w"))
             ops.colsum(du16, ar.grad(k + "ca.o.b"))
             dqc = torch.empty_like(qc)
             dkvc = torch.empty_like(kvc)
             ops.attention_bwd(qc, kvc, kvc, a_c, d_ac, lse_c, dqc, dkvc, dkvc, B=B, H=Hh, Sq=T, Sk=S, q_col0=0,
-                              k_col0=0, v_col0=D, dq_col0=0, dk_col0=0, dv_col0=D)
+                              k_col0=0, v_col0=D, dq_col0=0, dk_col0=0, dv_col0=D, drop=dr.site(j, 2))
             d_h1 = ops.gemm(dqc, ar.w16(k + "ca.q.w"), b_mn=True)
             ops.gemm(dqc, h1_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.q.w"))
             ops.colsum(dqc, ar.grad(k + "ca.q.b"))
@@ -423,13 +459,15 @@ class CrullerEngine:
             ops.colsum(dkvc, ar.span(k + "ca.k.b", k + "ca.v.b", "grad"))
             # self-attention LN
             du32, du16 = ops.layernorm_bwd(u1, m1, r1, ar.w32(k + "sa_ln.w"), ar.grad(k + "sa_ln.w"),
-                                           ar.grad(k + "sa_ln.b"), dy16=d_h1, dy32=du32, dx32=du32, dx16=du16)
+                                           ar.grad(k + "sa_ln.b"), dy16=d_h1, dy32=du32, dx32=du32, dx16=du16,
+                                           out_drop=dr.site(j, 1))
             d_as = ops.gemm(du16, ar.w16(k + "sa.o.w"), b_mn=True)
             ops.gemm(du16, a_s, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "sa.o.w"))
             ops.colsum(du16, ar.grad(k + "sa.o.b"))
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv, qkv, qkv, a_s, d_as, lse_s, dqkv, dqkv, dqkv, B=B, H=Hh, Sq=T, Sk=T, q_col0=0,
-                              k_col0=D, v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D, causal=True)
+                              k_col0=D, v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D, causal=True,
+                              drop=dr.site(j, 0))
             wqkv = ar.span(k + "sa.q.w", k + "sa.v.w", "w16").view(3 * D, D)
             dy16 = ops.gemm(dqkv, wqkv, b_mn=True)
             ops.gemm(dqkv, h0_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
@@ -439,7 +477,8 @@ class CrullerEngine:
             st.layers[j] = None
         x_emb, me, re_ = st.emb
         dx_emb, _ = ops.layernorm_bwd(x_emb, me, re_, ar.w32("dec.ln_emb.w"), ar.grad("dec.ln_emb.w"),
-                                      ar.grad("dec.ln_emb.b"), dy16=dy16, dy32=dy32, want_bf16=False)
+                                      ar.grad("dec.ln_emb.b"), dy16=dy16, dy32=dy32, want_bf16=False,
+                                      in_drop=dr.emb())
         ops.embed_bwd(st.ids, dx_emb, ar.grad("dec.tok"), ar.grad("dec.pos"), pos_offset=2, scale=1.0,
                       padding_idx=cfg.pad_token_id)
         if self._grad_ready_hook is not None:

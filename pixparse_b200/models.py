@@ -351,6 +351,12 @@ class BartForCausalLMB200(nn.Module):
     def get_input_embeddings(self):
         return self.model.decoder.embed_tokens
 
+    def set_dropout(self, dropout=0.0, attention_dropout=None, activation_dropout=None):
+        """Override the dropout rates restated from the public bart config (parity runs use 0)."""
+        self.config.dropout = float(dropout)
+        self.config.attention_dropout = float(dropout if attention_dropout is None else attention_dropout)
+        self.config.activation_dropout = float(dropout if activation_dropout is None else activation_dropout)
+
     def forward(self, *a, **kw):
         raise RuntimeError("BartForCausalLMB200 holds parameters only; call TextDecoderHf / Cruller")
 

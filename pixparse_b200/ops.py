@@ -20,7 +20,7 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=None, bias=None, aux=None,
-         splits=0, block_n=0, M=None, N=None, K=None):
+         splits=0, block_n=0, M=None, N=None, K=None, drop=None):
     """D[M,N] = sum_k A(m,k) B(n,k) on the tcgen05 path.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16;  b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
@@ -41,6 +41,11 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=Non
             out = torch.zeros((M, N), device=a.device, dtype=F32)
         else:
             out = torch.empty((M, N), device=a.device, dtype=BF16)
+    if drop is not None and drop[0] > 0.0:     # drop = (p, seed): dropout fused into the epilogue
+        call("b200_gemm_bf16_dropout", ptr(a), _ld(a), int(a_mn), ptr(b), _ld(b), int(b_mn), M, N, K, epi,
+             ptr(out), _ld(out), ptr(out2), _ld(out2) if out2 is not None else 0, ptr(bias),
+             ptr(aux), _ld(aux) if aux is not None else 0, splits, block_n, float(drop[0]), int(drop[1]), stream())
+        return out
     call("b200_gemm_bf16", ptr(a), _ld(a), int(a_mn), ptr(b), _ld(b), int(b_mn), M, N, K, epi,
          ptr(out), _ld(out), ptr(out2), _ld(out2) if out2 is not None else 0, ptr(bias),
          ptr(aux), _ld(aux) if aux is not None else 0, splits, block_n, stream())
@@ -48,7 +53,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=Non
 
 
 def attention_fwd(q, k, v, *, B, H, Sq, Sk, q_col0=0, k_col0=0, v_col0=0, causal=False, scale=None, out=None,
-                  lse=None):
+                  lse=None, drop=None):
     """q/k/v: 2-D bf16 views [B*S, row_width]; head h lives at columns [col0 + 64h, col0 + 64h + 64)."""
     dh = 64
     if scale is None:
@@ -57,6 +62,11 @@ def attention_fwd(q, k, v, *, B, H, Sq, Sk, q_col0=0, k_col0=0, v_col0=0, causal
         out = torch.empty((B * Sq, H * dh), device=q.device, dtype=BF16)
     if lse is None:
         lse = torch.empty((B, H, Sq), device=q.device, dtype=F32)
+    if drop is not None and drop[0] > 0.0:
+        call("b200_attention_fwd_dropout", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
+             ptr(out), _ld(out), ptr(lse), B, H, Sq, Sk, dh, int(causal), float(scale), float(drop[0]), int(drop[1]),
+             stream())
+        return out, lse
     call("b200_attention_fwd", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
          ptr(out), _ld(out), ptr(lse), B, H, Sq, Sk, dh, int(causal), float(scale), stream())
     return out, lse
@@ -66,7 +76,7 @@ _att_ws = {}
 
 
 def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, q_col0=0, k_col0=0, v_col0=0, do_col0=0,
-                  dq_col0=0, dk_col0=0, dv_col0=0, causal=False, scale=None):
+                  dq_col0=0, dk_col0=0, dv_col0=0, causal=False, scale=None, drop=None):
     """Gradients of attention_fwd. dq/dk/dv are caller-provided bf16 2-D buffers laid out like q/k/v."""
     dh = 64
     if scale is None:
@@ -77,31 +87,50 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, q_col0=0, k
     if ws is None or ws.numel() < need:
         ws = torch.empty((need,), device=q.device, dtype=torch.uint8)
         _att_ws[key] = ws
+    if drop is not None and drop[0] > 0.0:
+        call("b200_attention_bwd_dropout", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
+             ptr(o), _ld(o), ptr(d_o), _ld(d_o), do_col0, ptr(lse), ptr(dq), _ld(dq), dq_col0, ptr(dk), _ld(dk),
+             dk_col0, ptr(dv), _ld(dv), dv_col0, ptr(ws), B, H, Sq, Sk, dh, int(causal), float(scale), float(drop[0]),
+             int(drop[1]), stream())
+        return dq, dk, dv
     call("b200_attention_bwd", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
          ptr(o), _ld(o), ptr(d_o), _ld(d_o), do_col0, ptr(lse), ptr(dq), _ld(dq), dq_col0, ptr(dk), _ld(dk), dk_col0,
          ptr(dv), _ld(dv), dv_col0, ptr(ws), B, H, Sq, Sk, dh, int(causal), float(scale), stream())
     return dq, dk, dv
 
 
-def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False):
+def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False, drop=None):
     rows, dim = x.shape
     assert x.dtype == F32 and x.is_contiguous()
     y16 = torch.empty((rows, dim), device=x.device, dtype=BF16) if want_bf16 else None
     y32 = torch.empty((rows, dim), device=x.device, dtype=F32) if want_f32 else None
     mean = torch.empty((rows,), device=x.device, dtype=F32)
     rstd = torch.empty((rows,), device=x.device, dtype=F32)
+    if drop is not None and drop[0] > 0.0:
+        call("b200_layernorm_fwd_dropout", ptr(x), ptr(gamma), ptr(beta), ptr(y16), ptr(y32), ptr(mean), ptr(rstd),
+             rows, dim, float(eps), float(drop[0]), int(drop[1]), stream())
+        return y16, y32, mean, rstd
     call("b200_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(y16), ptr(y32), ptr(mean), ptr(rstd), rows, dim,
          float(eps), stream())
     return y16, y32, mean, rstd
 
 
 def layernorm_bwd(x, mean, rstd, gamma, dgamma, dbeta, *, dy16=None, dy32=None, dres32=None, dx32=None, dx16=None,
-                  want_f32=True, want_bf16=True):
+                  want_f32=True, want_bf16=True, in_drop=None, out_drop=None):
     rows, dim = x.shape
     if dx32 is None and want_f32:
         dx32 = torch.empty((rows, dim), device=x.device, dtype=F32)
     if dx16 is None and want_bf16:
         dx16 = torch.empty((rows, dim), device=x.device, dtype=BF16)
+    i_on = in_drop is not None and in_drop[0] > 0.0
+    o_on = out_drop is not None and out_drop[0] > 0.0
+    if i_on or o_on:
+        ip, iseed = in_drop if i_on else (0.0, 0)
+        op_, oseed = out_drop if o_on else (0.0, 0)
+        call("b200_layernorm_bwd_dropout", ptr(dy16), ptr(dy32), ptr(dres32), ptr(x), ptr(mean), ptr(rstd), ptr(gamma),
+             ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, dim, float(ip), int(iseed), float(op_), int(oseed),
+             stream())
+        return dx32, dx16
     call("b200_layernorm_bwd", ptr(dy16), ptr(dy32), ptr(dres32), ptr(x), ptr(mean), ptr(rstd), ptr(gamma),
          ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, dim, stream())
     return dx32, dx16

@@ -76,6 +76,7 @@ def test_b200_train_steps_match_reference_golden(cuda_lib, name):
     ours = models.Cruller(cfg)
     ours.text_decoder.trunk.resize_token_embeddings(g["vocab"])
     ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.text_decoder.trunk.set_dropout(0.0)     # parity runs: the oracle is built with dropout off
     ours.to("cuda")
     eng = engine_for(ours)
     opt = FusedAdamW(ours, eng, lr=o["lr"], betas=tuple(o["betas"]), eps=o["eps"])

@@ -21,6 +21,7 @@ def _build_pair(name, vocab=50267, seed=0):
     ours = models.Cruller(cfg)
     ours.text_decoder.trunk.resize_token_embeddings(vocab)
     ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.text_decoder.trunk.set_dropout(0.0)     # parity runs: the oracle is built with dropout off
     ours.to(DEV)
     return ref, ours
 
