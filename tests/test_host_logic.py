@@ -102,3 +102,13 @@ def test_synthetic_batch_layout():
     assert torch.equal(img, img2)
     pages = synthetic.synthetic_pages_u8(2, 110, 85, seed=0)
     assert pages.dtype == torch.uint8 and pages.shape == (2, 110, 85)
+
+
+def test_cer_wer_edit_distance():
+    from pixparse_b200.ocr_utils import cer, wer
+    assert cer(["hello world"], ["hello world"]) == 0.0
+    assert cer(["abcd"], ["abed"]) == pytest.approx(0.25)
+    assert cer(["abcd"], [""]) == pytest.approx(1.0)
+    assert wer(["the quick brown fox"], ["the quick fox"]) == pytest.approx(0.25)
+    assert wer(["a b", "c d"], ["a x", "c d"]) == pytest.approx(0.25)
+    assert cer(["<pad>ab  c<pad>"], ["ab c"]) == 0.0       # <pad> removed, whitespace collapsed / stripped
