@@ -288,6 +288,9 @@ def run_b200_arm(args):
 
 
 def main():
+    # keep stdout to the single JSON line: some boxes export NCCL_DEBUG=VERSION, which makes NCCL print a banner there
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

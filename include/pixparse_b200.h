@@ -118,6 +118,15 @@ int b200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_
                     const void* segments, int num_segments, const float* norm_stats, float grad_scale, float lr,
                     float beta1, float beta2, float eps, int step, int zero_grad, void* stream);
 
+/* ---- on-device page preprocessing ------------------------------------------------------
+ * uint8 'L' pages [B, Hin, Win] (page_stride bytes apart) -> fp32 [B, 1, Hout, Wout]:
+ * ToTensor -> Resize(BICUBIC, antialias=True) -> Normalize(mean, std), i.e. the transforms.Compose built in
+ * task/task_cruller_pretrain.py:132-143 (ATen _upsample_bicubic2d_aa). workspace: b200_preprocess_workspace_bytes().
+ */
+long long b200_preprocess_workspace_bytes(int Hout, int Wout);
+int b200_preprocess_pages(const void* pages_u8, int B, int Hin, int Win, long long page_stride, float* out, int Hout,
+                          int Wout, float mean, float std_, void* workspace, void* stream);
+
 /* ---- dropout-fused variants ------------------------------------------------------------------------
  * BART trains with dropout live (bart-base: dropout = attention_dropout = activation_dropout = 0.1; the reference
  * never calls model.eval() in train_step). Masks are stateless: keep(seed, element index) from a

@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200_grad_norm": [_P, _L, _P, _P, _F, _F, _P],
     "b200_grad_norm_workspace_floats": [],
     "b200_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _I, _P, _F, _F, _F, _F, _F, _I, _I, _P],
+    "b200_preprocess_pages": [_P, _I, _I, _I, _L, _P, _I, _I, _F, _F, _P, _P],
     "b200_gemm_bf16_dropout": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _F, _U, _P],
     "b200_layernorm_fwd_dropout": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _U, _P],
     "b200_layernorm_bwd_dropout": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U, _F, _U, _P],
@@ -83,6 +84,8 @@ def _declare(l):
         fn.restype = ctypes.c_int
     l.b200_attention_bwd_workspace_bytes.argtypes = [_I, _I, _I]
     l.b200_attention_bwd_workspace_bytes.restype = ctypes.c_longlong
+    l.b200_preprocess_workspace_bytes.argtypes = [_I, _I]
+    l.b200_preprocess_workspace_bytes.restype = ctypes.c_longlong
 
 
 def check(rc, what):

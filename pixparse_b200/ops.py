@@ -225,3 +225,17 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, segments, num_se
     call("b200_adamw_step", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), ptr(params_bf16),
          params.numel(), ptr(segments), num_segments, ptr(norm_stats), float(grad_scale), float(lr), float(beta1),
          float(beta2), float(eps), int(step), int(zero_grad), stream())
+
+
+def preprocess_pages(pages_u8, out_size, mean, std, out=None):
+    """uint8 grayscale pages [B, Hin, Win] on the device -> normalised fp32 [B, 1, Hout, Wout] (antialiased bicubic)."""
+    assert pages_u8.dtype == torch.uint8 and pages_u8.dim() == 3 and pages_u8.is_contiguous()
+    B, Hin, Win = pages_u8.shape
+    Hout, Wout = out_size
+    if out is None:
+        out = torch.empty((B, 1, Hout, Wout), device=pages_u8.device, dtype=F32)
+    ws = torch.empty((_lib.lib().b200_preprocess_workspace_bytes(Hout, Wout),), device=pages_u8.device,
+                     dtype=torch.uint8)
+    call("b200_preprocess_pages", ptr(pages_u8), B, Hin, Win, Hin * Win, ptr(out), Hout, Wout, float(mean), float(std),
+         ptr(ws), stream())
+    return out

@@ -26,7 +26,8 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_python_binding_table_matches_header():
     from pixparse_b200 import _lib
     declared = set(_header_functions())
-    bound = set(_lib.SIGNATURES) | {"b200_last_error", "b200_attention_bwd_workspace_bytes"}
+    bound = set(_lib.SIGNATURES) | {"b200_last_error", "b200_attention_bwd_workspace_bytes",
+                                     "b200_preprocess_workspace_bytes"}
     assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
 
 

@@ -273,3 +273,20 @@ def test_grad_norm_and_adamw(cuda_lib):
         assert (p - pr.detach()).abs().max().item() < 2e-6
         assert torch.equal(p16, p.bfloat16())
         assert g.abs().max().item() == 0.0      # zero_grad fused
+
+
+@pytest.mark.parametrize("Hin,Win,Hout,Wout", [(1100, 850, 576, 448), (330, 250, 576, 448), (64, 48, 64, 48),
+                                                 (1754, 1240, 798, 616)])
+def test_page_preprocess_matches_torchvision(cuda_lib, Hin, Win, Hout, Wout):
+    """ToTensor -> Resize(BICUBIC, antialias=True) -> Normalize as task_cruller_pretrain.py:132-143 builds it."""
+    import torchvision.transforms as T
+    from PIL import Image
+    from pixparse_b200 import ops, synthetic
+    pages = synthetic.synthetic_pages_u8(2, Hin, Win, seed=3)
+    mean, std = 0.449164, 0.268570
+    tf = T.Compose([T.ToTensor(), T.Resize((Hout, Wout), interpolation=T.InterpolationMode.BICUBIC, antialias=True),
+                    T.Normalize(mean=mean, std=std)])
+    ref = torch.stack([tf(Image.fromarray(p.numpy(), mode="L")) for p in pages])
+    out = ops.preprocess_pages(pages.cuda(), (Hout, Wout), mean, std)
+    assert out.shape == ref.shape
+    assert (out.cpu() - ref).abs().max().item() < 2e-5
