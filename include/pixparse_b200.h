@@ -58,6 +58,15 @@ int b200_attention_fwd(const void* q, long long ldq, int q_col0, const void* k, 
                        const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
                        int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
 
+/* same with explicit batch strides (elements; 0 = dense [B, S, ld]) -- used by the KV-cached greedy decode, whose
+ * self-attention keys/values live in a pre-allocated [B, T_max, 2D] cache (utils/ocr_utils.py:165-197 re-feeds the
+ * whole prefix instead; models/text_decoder_hf.py:69-70 is the past_key_values branch this serves) */
+int b200_attention_fwd_strided(const void* q, long long ldq, long long q_bstride, int q_col0, const void* k,
+                               long long ldk, long long k_bstride, int k_col0, const void* v, long long ldv,
+                               long long v_bstride, int v_col0, void* out, long long ld_out, long long out_bstride,
+                               float* lse, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
+                               void* stream);
+
 /* backward: dq/dk/dv (bf16, strided like q/k/v) from d_o; `o` and `lse` are the forward outputs.
  * workspace: b200_attention_bwd_workspace_bytes(B, H, Sq) bytes of device memory (fp32 dQ accumulator + row sums). */
 long long b200_attention_bwd_workspace_bytes(int B, int H, int Sq);

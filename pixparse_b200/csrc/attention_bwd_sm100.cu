@@ -15,7 +15,8 @@
 
 namespace b200 {
 
-int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld, int box_rows);
+int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld, int box_rows,
+                  long long batch_stride);
 
 constexpr int AB_T = 128;                 // tile edge (queries and keys)
 constexpr int AB_D = 64;
@@ -505,10 +506,10 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
 
   CUtensorMap tq, tk, tv, tdo, tdq;
   int rc;
-  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)W, ldq, 128))) return rc;
-  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)W, ldk, 128))) return rc;
-  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)W, ldv, 128))) return rc;
-  if ((rc = make_att_tmap(&tdo, d_o, B, Sq, do_col0 + (long long)W, ld_do, 128))) return rc;
+  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)W, ldq, 128, 0))) return rc;
+  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)W, ldk, 128, 0))) return rc;
+  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)W, ldv, 128, 0))) return rc;
+  if ((rc = make_att_tmap(&tdo, d_o, B, Sq, do_col0 + (long long)W, ld_do, 128, 0))) return rc;
   {
     // fp32 dQ accumulator viewed as [B][Sq][W]; box = 32 floats x 128 rows (rows beyond Sq are clipped)
     uint64_t dims[3] = {(uint64_t)W, (uint64_t)Sq, (uint64_t)B};

@@ -39,8 +39,8 @@ struct AttFwdParams {
   int B, H, Sq, Sk;
   int causal;
   float scale_log2;        // softmax scale * log2(e)
-  bf16* out;               // [B, Sq, ld_out] bf16, head h at column h*64
-  long long ld_out;
+  bf16* out;               // token (b, q) at out + b * out_bstride + q * ld_out, head h at column h*64
+  long long ld_out, out_bstride;
   float* lse;              // [B, H, Sq] natural-log logsumexp of the scaled scores
   int q_col0, k_col0, v_col0;   // column offsets of head 0 inside the Q / K / V row
   uint32_t drop_threshold16, drop_seed;   // attention-probability dropout (BART attention_dropout); 0 = off
@@ -260,7 +260,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
     // tcgen05.ld is warp-collective: every lane issues the loads, only the stores are predicated
     const bool row_ok = qidx < p.Sq;
-    bf16* orow = p.out + ((long long)b * p.Sq + (row_ok ? qidx : 0)) * p.ld_out + h * ATT_D;
+    bf16* orow = p.out + (long long)b * p.out_bstride + (long long)(row_ok ? qidx : 0) * p.ld_out + h * ATT_D;
 #pragma unroll 1
     for (int c = 0; c < ATT_D / 32; ++c) {
       uint32_t r[32];
@@ -288,9 +288,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 // 3-D tensor map over a [B, S, width] bf16 activation whose rows are `ld` elements apart; box = 64 x box_rows x 1
-int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld, int box_rows) {
+int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld, int box_rows,
+                  long long batch_stride) {
   uint64_t dims[3] = {(uint64_t)width, (uint64_t)S, (uint64_t)B};
-  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)S};
+  if (batch_stride <= 0) batch_stride = ld * S;      // densely packed [B, S, ld]
+  if (B == 1) batch_stride = ld * S;                 // irrelevant for a single batch; keep it a valid multiple of 16 B
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)batch_stride * 2};
   uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return make_tmap(m, base, TMA_BF16, 3, dims, strides, box, TMA_SWIZZLE_128B);
 }
@@ -302,7 +305,8 @@ using namespace b200;
 static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
                               const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse, int B,
                               int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
-                              unsigned int drop_seed, void* stream);
+                              unsigned int drop_seed, void* stream, long long q_bs = 0, long long k_bs = 0,
+                              long long v_bs = 0, long long out_bs = 0);
 
 extern "C" int b200_attention_fwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
                                   const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
@@ -320,10 +324,21 @@ extern "C" int b200_attention_fwd_dropout(const void* q, long long ldq, int q_co
                             causal, scale, drop_p, drop_seed, stream);
 }
 
+// KV-cache friendly variant: explicit batch strides (elements) for q / k / v / out; 0 = densely packed [B, S, ld]
+extern "C" int b200_attention_fwd_strided(const void* q, long long ldq, long long q_bstride, int q_col0, const void* k,
+                                          long long ldk, long long k_bstride, int k_col0, const void* v, long long ldv,
+                                          long long v_bstride, int v_col0, void* out, long long ld_out,
+                                          long long out_bstride, float* lse, int B, int H, int Sq, int Sk, int head_dim,
+                                          int causal, float scale, void* stream) {
+  return attention_fwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ld_out, lse, B, H, Sq, Sk, head_dim,
+                            causal, scale, 0.f, 0u, stream, q_bstride, k_bstride, v_bstride, out_bstride);
+}
+
 static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
                               const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse, int B,
                               int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
-                              unsigned int drop_seed, void* stream) {
+                              unsigned int drop_seed, void* stream, long long q_bs, long long k_bs, long long v_bs,
+                              long long out_bs) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(head_dim == ATT_D, "b200_attention_fwd: head_dim %d unsupported (only 64)", head_dim);
   B200_CHECK_ARG(q && k && v && out && B > 0 && H > 0 && Sq > 0 && Sk > 0, "b200_attention_fwd: bad arguments");
@@ -334,13 +349,15 @@ static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const vo
   if (causal) B200_CHECK_ARG(Sk >= Sq, "b200_attention_fwd: causal attention needs Sk >= Sq");
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)H * ATT_D, ldq, ATT_BM))) return rc;
-  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)H * ATT_D, ldk, ATT_BN))) return rc;
-  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)H * ATT_D, ldv, ATT_BN))) return rc;
+  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)H * ATT_D, ldq, ATT_BM, q_bs))) return rc;
+  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)H * ATT_D, ldk, ATT_BN, k_bs))) return rc;
+  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)H * ATT_D, ldv, ATT_BN, v_bs))) return rc;
   AttFwdParams p;
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out; p.lse = lse;
+  p.out_bstride = out_bs > 0 ? out_bs : (long long)Sq * ld_out;
+  B200_CHECK_ARG(q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && out_bs % 8 == 0, "b200_attention_fwd: batch strides must be multiples of 8 elements");
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "b200_attention_fwd: dropout p must be in [0, 1)");
   p.drop_threshold16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;

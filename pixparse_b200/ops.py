@@ -53,15 +53,19 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=Non
 
 
 def attention_fwd(q, k, v, *, B, H, Sq, Sk, q_col0=0, k_col0=0, v_col0=0, causal=False, scale=None, out=None,
-                  lse=None, drop=None):
+                  lse=None, drop=None, q_bs=0, kv_bs=0, out_bs=0, want_lse=True):
     """q/k/v: 2-D bf16 views [B*S, row_width]; head h lives at columns [col0 + 64h, col0 + 64h + 64)."""
     dh = 64
     if scale is None:
         scale = dh ** -0.5
     if out is None:
         out = torch.empty((B * Sq, H * dh), device=q.device, dtype=BF16)
-    if lse is None:
+    if lse is None and want_lse:
         lse = torch.empty((B, H, Sq), device=q.device, dtype=F32)
+    if q_bs or kv_bs or out_bs:      # explicit batch strides (KV cache): token stride = row stride of the 2-D view
+        call("b200_attention_fwd_strided", ptr(q), _ld(q), q_bs, q_col0, ptr(k), _ld(k), kv_bs, k_col0, ptr(v), _ld(v),
+             kv_bs, v_col0, ptr(out), _ld(out), out_bs, ptr(lse), B, H, Sq, Sk, dh, int(causal), float(scale), stream())
+        return out, lse
     if drop is not None and drop[0] > 0.0:
         call("b200_attention_fwd_dropout", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
              ptr(out), _ld(out), ptr(lse), B, H, Sq, Sk, dh, int(causal), float(scale), float(drop[0]), int(drop[1]),
