@@ -104,6 +104,21 @@ class _Saved:
     pass
 
 
+class DecodeCache:
+    """KV cache of one greedy-decoding session: per decoder layer the self-attention keys | values of
+    every generated position ([B, T_max, 2D], appended in place) and the cross-attention K | V projection of the image
+    tokens (computed at the first step). It is what TextDecoderHf returns as ``past_key_values``."""
+
+    def __init__(self, num_layers, B, t_max, D, device):
+        self.t_max = t_max
+        self.length = 0
+        self.self_kv = [torch.empty((B, t_max, 2 * D), device=device, dtype=torch.bfloat16) for _ in range(num_layers)]
+        self.cross_kv = [None] * num_layers
+
+    def get_seq_length(self):
+        return self.length
+
+
 class CrullerEngine:
     def __init__(self, module):
         from . import models
@@ -340,14 +355,19 @@ class CrullerEngine:
             p = (self.pa, self.p, self.pa, self.p, self.pact, self.p)[k]
             return (p, self._seed(1 + 8 * layer + k))
 
-    def decoder_forward(self, ids, enc16, B, S, save):
+    def decoder_forward(self, ids, enc16, B, S, save, cache=None):
+        """cache: DecodeCache for incremental decoding (inference only): `ids` are the NEW tokens, positions continue
+        at cache.length, self-attention keys / values are appended to the cache, the cross-attention K / V projections
+        of the image tokens are computed once and reused."""
         ar, bart = self.arena, self.bart
         cfg = bart.config
         D, Hh, nl = cfg.d_model, cfg.decoder_attention_heads, cfg.decoder_layers
         eps = 1e-5
         T = ids.shape[1]
         assert ids.shape[0] == B
-        assert T <= cfg.max_position_embeddings, "sequence longer than max_position_embeddings"
+        past = cache.length if cache is not None else 0
+        assert past + T <= cfg.max_position_embeddings, "sequence longer than max_position_embeddings"
+        assert not (save and cache is not None), "the KV cache is an inference-only path"
         M = B * T
         V = ar.index["dec.tok"][2][0]
         if ids.dtype != torch.int64 or not ids.is_contiguous():
@@ -357,7 +377,7 @@ class CrullerEngine:
         self._dropout_calls += 1
         dr = CrullerEngine._Drop(cfg, self.dropout_seed + 7919 * self._dropout_calls, save and bart.training)
         st.drop = dr
-        x_emb = ops.embed_fwd(ids, ar.w32("dec.tok"), ar.w32("dec.pos"), pos_offset=2, scale=1.0)
+        x_emb = ops.embed_fwd(ids, ar.w32("dec.tok"), ar.w32("dec.pos"), pos_offset=2 + past, scale=1.0)
         h16, h32, me, re_ = ops.layernorm_fwd(x_emb, ar.w32("dec.ln_emb.w"), ar.w32("dec.ln_emb.b"), eps, want_f32=True,
                                               drop=dr.emb())
         st.emb = (x_emb, me, re_)
@@ -368,8 +388,17 @@ class CrullerEngine:
             wqkv = ar.span(k + "sa.q.w", k + "sa.v.w", "w16").view(3 * D, D)
             bqkv = ar.span(k + "sa.q.b", k + "sa.v.b", "w32")
             qkv = ops.gemm(h16, wqkv, bias=bqkv)
-            a_s, lse_s = ops.attention_fwd(qkv, qkv, qkv, B=B, H=Hh, Sq=T, Sk=T, q_col0=0, k_col0=D, v_col0=2 * D,
-                                           causal=True, drop=dr.site(j, 0))
+            if cache is not None:
+                # append this step's keys / values, attend over the whole cached prefix (causal inside the new block)
+                kvbuf = cache.self_kv[j]                                      # [B, T_max, 2D]
+                kvbuf[:, past:past + T, :].copy_(qkv.view(B, T, 3 * D)[:, :, D:])
+                kv2d = kvbuf.view(B * cache.t_max, 2 * D)
+                a_s, lse_s = ops.attention_fwd(qkv, kv2d, kv2d, B=B, H=Hh, Sq=T, Sk=past + T, q_col0=0, k_col0=0,
+                                               v_col0=D, causal=True, q_bs=T * 3 * D, kv_bs=cache.t_max * 2 * D,
+                                               out_bs=T * D, want_lse=False)
+            else:
+                a_s, lse_s = ops.attention_fwd(qkv, qkv, qkv, B=B, H=Hh, Sq=T, Sk=T, q_col0=0, k_col0=D,
+                                               v_col0=2 * D, causal=True, drop=dr.site(j, 0))
             u1 = torch.empty_like(h32)
             ops.gemm(a_s, ar.w16(k + "sa.o.w"), bias=ar.w32(k + "sa.o.b"), epi=EPI_RESID_F32, aux=h32, out=u1,
                      drop=dr.site(j, 1))
@@ -379,7 +408,12 @@ class CrullerEngine:
             qc = ops.gemm(h1_16, ar.w16(k + "ca.q.w"), bias=ar.w32(k + "ca.q.b"))
             wkv = ar.span(k + "ca.k.w", k + "ca.v.w", "w16").view(2 * D, D)
             bkv = ar.span(k + "ca.k.b", k + "ca.v.b", "w32")
-            kvc = ops.gemm(enc16, wkv, bias=bkv)
+            if cache is not None and cache.cross_kv[j] is not None:
+                kvc = cache.cross_kv[j]
+            else:
+                kvc = ops.gemm(enc16, wkv, bias=bkv)
+                if cache is not None:
+                    cache.cross_kv[j] = kvc
             a_c, lse_c = ops.attention_fwd(qc, kvc, kvc, B=B, H=Hh, Sq=T, Sk=S, q_col0=0, k_col0=0, v_col0=D,
                                            drop=dr.site(j, 2))
             u2 = torch.empty_like(h32)
@@ -401,6 +435,8 @@ class CrullerEngine:
                 st.layers.append((h16, qkv, a_s, lse_s, u1, m1, r1, h1_16, qc, kvc, a_c, lse_c, u2, m2, r2, h2_16,
                                   hpre, g, u3, m3, r3))
             h16, h32 = h3_16, h3_32
+        if cache is not None:
+            cache.length = past + T
         ldv = _round_up(V, 8)
         logits = torch.empty((M, ldv), device=h16.device, dtype=torch.bfloat16)
         ops.gemm(h16, ar.w16("dec.tok"), epi=EPI_STORE_BF16, out=logits, N=V)
@@ -495,20 +531,28 @@ class CrullerEngine:
         B = image.shape[0]
         return enc16.view(B, -1, enc16.shape[-1])
 
-    def decode_logits(self, input_ids, encoder_hidden_states, attention_mask=None):
-        """TextDecoderHf.forward (teacher-forced / uncached greedy step): logits (B, T, V) bf16.
+    def decode_logits(self, input_ids, encoder_hidden_states, attention_mask=None, past_key_values=None,
+                      use_cache=False):
+        """TextDecoderHf.forward (teacher-forced / greedy step): logits (B, T, V) bf16 [, DecodeCache].
 
         attention_mask: the reference builds it as input_ids != pad (text_decoder_hf.py:68). With right padding and a
-        causal mask PAD keys can only influence PAD queries, so it does not change any non-pad position."""
+        causal mask PAD keys can only influence PAD queries, so it does not change any non-pad position.
+        use_cache / past_key_values: the incremental path of prepare_inputs_for_inference (text_decoder_hf.py:69-70):
+        only the new tokens are passed, keys / values of the prefix come from the cache."""
         self.refresh_shadow()
         B, S, D = encoder_hidden_states.shape
         enc16 = encoder_hidden_states.reshape(B * S, D)
         if enc16.dtype != torch.bfloat16:
             enc16 = enc16.to(torch.bfloat16)
         enc16 = enc16.contiguous()
-        logits, _ = self.decoder_forward(input_ids, enc16, B, S, save=False)
+        cache = past_key_values
+        if cache is None and use_cache:
+            cfg = self.bart.config
+            cache = DecodeCache(cfg.decoder_layers, B, cfg.max_position_embeddings, cfg.d_model, enc16.device)
+        logits, _ = self.decoder_forward(input_ids, enc16, B, S, save=False, cache=cache)
         V = self.arena.index["dec.tok"][2][0]
-        return logits.view(B, input_ids.shape[1], -1)[:, :, :V]
+        logits = logits.view(B, input_ids.shape[1], -1)[:, :, :V]
+        return (logits, cache) if (use_cache or past_key_values is not None) else logits
 
     def forward_logits(self, image, text_ids):
         """Cruller.forward. Under autograd the returned logits carry a backward that runs the fused kernels."""

@@ -431,7 +431,12 @@ class TextDecoderHf(nn.Module):
         from .engine import engine_for
         if output_attentions or output_hidden_states:
             raise NotImplementedError("attention maps / hidden states are never materialised by the fused kernels")
-        logits = engine_for(self).decode_logits(input_ids, encoder_hidden_states, attention_mask=attention_mask)
+        eng = engine_for(self)
+        if use_cache or past_key_values is not None:
+            logits, cache = eng.decode_logits(input_ids, encoder_hidden_states, attention_mask=attention_mask,
+                                              past_key_values=past_key_values, use_cache=True)
+            return CausalLMOutput(logits=logits, past_key_values=cache)
+        logits = eng.decode_logits(input_ids, encoder_hidden_states, attention_mask=attention_mask)
         return CausalLMOutput(logits=logits, past_key_values=None)
 
 

@@ -50,16 +50,24 @@ def get_next_token(next_token_logits, use_sample: bool = True, temperature: floa
     return next_token_id, probs
 
 
-def get_generated_tokens(model, tokenizer, encoder_outputs, device_env, max_recursion_length, prompt_token: str):
+def get_generated_tokens(model, tokenizer, encoder_outputs, device_env, max_recursion_length, prompt_token: str,
+                         use_cache: bool = False):
+    """use_cache=False is the reference loop (whole prefix re-fed each step). use_cache=True feeds only the last token
+    and carries ``past_key_values`` (the branch prepare_inputs_for_inference already has, text_decoder_hf.py:69-70):
+    same token ids, O(steps) instead of O(steps^2) decoder work."""
     task_prompt_id = tokenizer.trunk.encode(prompt_token, add_special_tokens=False)[0]
     device = device_env.device
     input_ids = torch.full((encoder_outputs.shape[0], 1), task_prompt_id, dtype=torch.long, device=device)
     finished = torch.zeros(input_ids.shape[0], dtype=torch.bool, device=device)
     eos_token_id = tokenizer.trunk.eos_token_id
+    past = None
     for _ in range(max_recursion_length):
         inputs = model.text_decoder.prepare_inputs_for_inference(
-            input_ids=input_ids, encoder_outputs=encoder_outputs, pad_token_id=tokenizer.trunk.pad_token_id)
+            input_ids=input_ids, encoder_outputs=encoder_outputs, pad_token_id=tokenizer.trunk.pad_token_id,
+            past_key_values=past, use_cache=True if use_cache else None)
         outputs = model.text_decoder.forward(**inputs)
+        if use_cache:
+            past = outputs.past_key_values
         next_token_logits = outputs.logits[:, -1, :]
         next_token_id, _ = get_next_token(next_token_logits, use_sample=False)
         finished |= next_token_id.squeeze(-1) == eos_token_id

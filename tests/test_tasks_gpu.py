@@ -123,3 +123,34 @@ def test_eval_ocr_greedy_decode_follows_oracle(cuda_lib):
     assert set(metrics["ocr_reconstruction"]) == {"wer", "cer"}
     avg = task.average_metrics({0: metrics, 1: metrics})
     assert avg["ocr_reconstruction"]["cer"] == pytest.approx(metrics["ocr_reconstruction"]["cer"])
+
+
+def test_kv_cached_greedy_decode_equals_uncached_loop(cuda_lib):
+    """cross-attention K/V projected once, self-attention K/V appended per step, one token per step; the
+    generated ids must equal the reference-style uncached loop (same kernels, same per-row arithmetic)."""
+    import time
+    from oracle import cruller_ref
+    from pixparse_b200 import models, synthetic
+    from pixparse_b200.framework import DeviceEnv
+    from pixparse_b200.ocr_utils import get_generated_tokens
+    from pixparse_b200.task_eval_ocr import TaskCrullerEvalOCR, TaskCrullerEvalOCRCfg
+    task = TaskCrullerEvalOCR(TaskCrullerEvalOCRCfg(model_name="cruller_test"), DeviceEnv(),
+                              tokenizer=synthetic.SyntheticBartTokenizer())
+    ref = cruller_ref.build_model("cruller_test", vocab_size=50267, seed=5)
+    with torch.no_grad():
+        ref.text_decoder.trunk.model.decoder.embed_tokens.weight.mul_(8.0)
+    task.resume_state_dict = ref.state_dict()
+    task.setup()
+    image, _, _ = synthetic.synthetic_batch(5, (64, 48), 12, seed=4)
+    with torch.inference_mode():
+        enc = task.model.image_encoder(image.cuda())
+        steps = 70       # crosses the 64-key tile boundary of the attention kernel
+        t0 = time.time()
+        ids_ref = get_generated_tokens(task.model, task.tokenizer, enc, task.device_env, steps, "<s_pretrain>")
+        torch.cuda.synchronize(); t1 = time.time()
+        ids_kv = get_generated_tokens(task.model, task.tokenizer, enc, task.device_env, steps, "<s_pretrain>",
+                                      use_cache=True)
+        torch.cuda.synchronize(); t2 = time.time()
+    assert ids_kv.shape == ids_ref.shape
+    assert torch.equal(ids_kv, ids_ref)
+    print(f"uncached {t1 - t0:.3f}s cached {t2 - t1:.3f}s for {ids_ref.shape[1] - 1} steps")
