@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpixparse_b200.so")
+LIB_PATH = os.environ.get("PIXPARSE_B200_LIB") or os.path.join(_HERE, "csrc", "libpixparse_b200.so")
 
 _lib = None
 

@@ -27,6 +27,15 @@ constexpr int AB_SMEM = 12 * AB_TILE + 256 + 1024;   // K, V, Q[2], dO[2], P(2),
 
 constexpr uint32_t TB_S = 0, TB_DP = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
 
+#ifdef AB_TRACE
+#define AB_STAMP(slot)                                                                     \
+  do {                                                                                     \
+    if (trace_on && t < 8) p.trace[(t * 16 + (slot))] = clock64();                         \
+  } while (0)
+#else
+#define AB_STAMP(slot) do { } while (0)
+#endif
+
 struct AttBwdParams {
   int B, H, Sq, Sk, causal;
   float scale, scale_log2;
@@ -36,6 +45,7 @@ struct AttBwdParams {
   bf16* dv; long long ld_dv; int dv_col0;
   int q_col0, k_col0, v_col0, do_col0;
   uint32_t drop_threshold16, drop_seed;   // attention-probability dropout of the forward pass (0 = off)
+  long long* trace;                       // bring-up builds only (-DAB_TRACE): clock64 stamps of CTA (3,0,0)
 };
 
 // Pipeline per query tile t (tensor pipe on the left, the 8 compute warps on the right run concurrently):
@@ -43,6 +53,7 @@ struct AttBwdParams {
 //     dV += P_t^T dO_t ; S_{t+1} .. (drain dQ_{t-1}: TMEM -> smem -> TMA reduce-add) ; stage B: dS_t = P_t*(dP_t - D)*scale -> smem
 //     dK += dS_t^T Q_t ; dQ_t = dS_t K ; dP_{t+1} ....... stage A of tile t+1 ...
 // so the MMAs of one stage always run under the exp / multiply work of the other stage.
+template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
@@ -179,7 +190,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint64_t dO_mn = make_smem_desc(smem_u32(sdO + s * AB_TILE), 16384, 1024);
         const uint64_t dQ_mn = make_smem_desc(smem_u32(sQ + s * AB_TILE), 16384, 1024);
         // ---- P_t ready: dV += P_t^T dO_t, then S_{t+1}
+#ifdef AB_TRACE
+        const bool trace_on = p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
+        AB_STAMP(8);
         mbar_wait(p_ready, t & 1);
+        AB_STAMP(9);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -195,7 +211,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           issue_s(t + 1);
         }
         // ---- dS_t ready: dK += dS_t^T Q_t, dQ_t = dS_t K, then dP_{t+1}
+        AB_STAMP(10);
         mbar_wait(ds_ready, t & 1);
+        AB_STAMP(11);
         tc_fence_after();
         // dS read K-major for dQ: 64-key chunk = k / 4, 32 bytes per step inside the 128-byte row
         const uint64_t dS_k0 = make_smem_desc(smem_u32(sdS), 16, 1024);
@@ -214,6 +232,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         __syncwarp();
         if (t + 1 < n_iter) issue_dp(t + 1);
+        AB_STAMP(12);
       }
       if (elect_one()) umma_commit(dkv_full);
       __syncwarp();
@@ -250,13 +269,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
     };
 
+    // per-row statistics of the NEXT query tile are fetched one iteration ahead: a dependent global load at the loop
+    // top costs ~900 cycles per tile (measured with the AB_TRACE build), a fifth of the whole iteration
+    auto load_stats = [&](int t, float& lse_raw, float& dsum_raw) {
+      const int qi = (i_begin + t) * AB_T + row;
+      const bool ok = t < n_iter && qi < p.Sq;
+      const long long idx = ((long long)b * p.H + h) * p.Sq + (ok ? qi : 0);
+      lse_raw = ok ? __ldg(p.lse + idx) : INFINITY;      // +inf -> P = 0 for padded query rows
+      dsum_raw = ok ? __ldg(p.dsum + idx) : 0.f;
+    };
+    float lse_next, dsum_next;
+    load_stats(0, lse_next, dsum_next);
     for (int t = 0; t < n_iter; ++t) {
       const int q0 = (i_begin + t) * AB_T;
       const int qidx = q0 + row;
-      const bool q_ok = qidx < p.Sq;
-      const long long stat_idx = ((long long)b * p.H + h) * p.Sq + (q_ok ? qidx : 0);
-      const float lse2 = q_ok ? p.lse[stat_idx] * kLog2e : INFINITY;   // +inf -> P = 0 for padded query rows
-      const float dsum = q_ok ? p.dsum[stat_idx] : 0.f;
+      const float lse2 = lse_next * kLog2e;
+      const float dsum = dsum_next;
+      load_stats(t + 1, lse_next, dsum_next);
       int kmax = p.Sk - 1;
       if (p.causal) kmax = min(kmax, qidx + shift);
       const bool need_mask = (k0 + AB_T > p.Sk) || (p.causal && (k0 + AB_T - 1 > q0 + shift));
@@ -264,7 +293,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
       // ---------------- stage A: P_t ----------------
       float pv[64];
+#ifdef AB_TRACE
+      const bool trace_on = p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+#endif
+      AB_STAMP(0);
       mbar_wait(s_full, t & 1);
+      AB_STAMP(1);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -288,6 +322,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t drop_row = (uint32_t)((((long long)b * p.H + h) * p.Sq + qidx) * ((p.Sk + 1) >> 1)) +
                                 (uint32_t)(kbase >> 1);
       const float drop_sc = dropout_scale(p.drop_threshold16);
+      AB_STAMP(2);
       if (t > 0) mbar_wait(p_free, (t - 1) & 1);      // dV_{t-1} no longer reads the P buffer
       {
         uint8_t* prow = sP + half * AB_TILE + row * 128;
@@ -296,7 +331,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           float q8[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) q8[e] = pv[8 * j + e];
-          if (p.drop_threshold16 != 0u) {      // dV uses the dropped probabilities
+          if (DROP) {      // dV uses the dropped probabilities
 #pragma unroll
             for (int e = 0; e < 8; e += 2)
               dropout_pair(p.drop_seed, drop_row + (uint32_t)((8 * j + e) >> 1), p.drop_threshold16, drop_sc, q8[e],
@@ -310,12 +345,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_ready);
+      AB_STAMP(3);
 
       // ---------------- dQ of the previous tile leaves while the tensor pipe works on dV_t / S_{t+1} ------------
       if (t > 0) drain_dq(t - 1);       // also guarantees dK_{t-1} / dQ_{t-1} no longer read the dS buffer
+      AB_STAMP(7);
 
       // ---------------- stage B: dS_t ----------------
+      AB_STAMP(4);
       mbar_wait(dp_full, t & 1);
+      AB_STAMP(5);
       tc_fence_after();
       {
         uint8_t* drow = sdS + half * AB_TILE + row * 128;
@@ -325,7 +364,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           tmem_ld_32x32(lane_addr + TB_DP + half * 64 + c * 32, rp);
           tmem_ld_wait();
           float dsv[32];
-          if (p.drop_threshold16 != 0u) {      // dS = P * (mask * dP - D) * scale
+          if (DROP) {      // dS = P * (mask * dP - D) * scale
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
               float g0 = __uint_as_float(rp[e]), g1 = __uint_as_float(rp[e + 1]);
@@ -349,6 +388,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
+      AB_STAMP(6);
     }
     if (n_iter > 0) {
       drain_dq(n_iter - 1);
@@ -435,6 +475,11 @@ __global__ void attention_dq_convert_kernel(const float* __restrict__ dq32, bf16
 }  // namespace b200
 
 using namespace b200;
+
+#ifdef AB_TRACE
+long long* g_ab_trace = nullptr;
+extern "C" int b200_debug_set_trace(long long* ptr) { g_ab_trace = ptr; return 0; }
+#endif
 
 extern "C" long long b200_attention_bwd_workspace_bytes(int B, int H, int Sq) {
   // fp32 dQ accumulator [B*Sq, H*64] followed by D [B, H, Sq]
@@ -527,14 +572,21 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
   B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "b200_attention_bwd: dropout p must be in [0, 1)");
   p.drop_threshold16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
   p.drop_seed = drop_seed;
+  p.trace = nullptr;
+#ifdef AB_TRACE
+  { extern long long* g_ab_trace; p.trace = g_ab_trace; }
+#endif
   static bool configured = false;
   if (!configured) {
-    e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attention_bwd)");
     configured = true;
   }
   dim3 grid((Sk + AB_T - 1) / AB_T, H, B);
-  attention_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
+  if (p.drop_threshold16 != 0u) attention_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
+  else attention_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
   B200_CHECK_LAUNCH("attention_bwd");
 
   {

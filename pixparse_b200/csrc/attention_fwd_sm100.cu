@@ -46,6 +46,7 @@ struct AttFwdParams {
   uint32_t drop_threshold16, drop_seed;   // attention-probability dropout (BART attention_dropout); 0 = off
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
@@ -239,7 +240,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
             }
             l_tile += p0 + p1;        // the softmax normaliser uses the un-dropped probabilities
-            if (p.drop_threshold16 != 0u)
+            if (DROP)
               dropout_pair(p.drop_seed, drop_row + (uint32_t)((k0 + c * 32 + 2 * e) >> 1), p.drop_threshold16, drop_sc,
                            p0, p1);
             pk[e] = pack_bf16(p0, p1);
@@ -364,12 +365,15 @@ static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const vo
   p.drop_seed = drop_seed;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attention_fwd)");
     configured = true;
   }
   dim3 grid((Sq + ATT_BM - 1) / ATT_BM, H, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
+  if (p.drop_threshold16 != 0u) attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
+  else attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
   B200_CHECK_LAUNCH("attention_fwd");
   return 0;
 }

@@ -66,7 +66,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 
 // dy = (dy16 ? dy16 : 0) + (dy32 ? dy32 : 0);   dx = LNbwd(dy) + (dres32 ? dres32 : 0)
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (fp32 atomics, one set per block)
-template <int NV>
+template <int NV, bool DROP>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ dres32,
                      const float* __restrict__ x, const float* __restrict__ mean_in,
@@ -104,7 +104,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy
         const float4 r = reinterpret_cast<const float4*>(dy32 + (size_t)row * D)[lane + 32 * i];
         d.x += r.x; d.y += r.y; d.z += r.z; d.w += r.w;
       }
-      if (in_thr != 0u) {      // the forward dropped this LayerNorm's OUTPUT: mask the incoming gradient the same way
+      if (DROP && in_thr != 0u) {      // the forward dropped this LayerNorm's OUTPUT: mask the incoming gradient the same way
         const uint32_t pair = (uint32_t)(((size_t)row * D + (size_t)(lane + 32 * i) * 4) >> 1);
         const float sc = dropout_scale(in_thr);
         dropout_pair(in_seed, pair, in_thr, sc, d.x, d.y);
@@ -132,7 +132,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy
       }
       if (dx32) reinterpret_cast<float4*>(dx32 + (size_t)row * D)[lane + 32 * i] = o;
       if (dx16) {
-        if (out_thr != 0u) {   // dx16 feeds the sub-layer whose output was dropped before the residual add
+        if (DROP && out_thr != 0u) {   // dx16 feeds the sub-layer whose output was dropped before the residual add
           const uint32_t pair = (uint32_t)(((size_t)row * D + (size_t)(lane + 32 * i) * 4) >> 1);
           const float sc = dropout_scale(out_thr);
           dropout_pair(out_seed, pair, out_thr, sc, o.x, o.y);
@@ -178,8 +178,13 @@ static int ln_bwd_launch(const bf16* dy16, const float* dy32, const float* dres3
   int grid = num_sms() * 4;
   const int need = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > need) grid = need;
-  layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy32, dres32, x, mean, rstd, gamma, dx32, dx16,
-                                                          dgamma, dbeta, rows, in_thr, in_seed, out_thr, out_seed);
+  if (in_thr != 0u || out_thr != 0u)
+    layernorm_bwd_kernel<NV, true><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy32, dres32, x, mean, rstd, gamma, dx32, dx16,
+                                                                  dgamma, dbeta, rows, in_thr, in_seed, out_thr,
+                                                                  out_seed);
+  else      // the common (encoder) case carries no dropout code at all
+    layernorm_bwd_kernel<NV, false><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy32, dres32, x, mean, rstd, gamma, dx32, dx16,
+                                                                   dgamma, dbeta, rows, 0u, 0u, 0u, 0u);
   B200_CHECK_LAUNCH("layernorm_bwd");
   return 0;
 }
