@@ -20,8 +20,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = trace.cpu().view(8, 16)
 base = int(t[0, 0])
-names = ["c:loop_top", "c:s_full", "c:exp_done", "c:p_ready_arrive", "c:before_dp_wait", "c:dp_full", "c:ds_ready_arrive",
-         "c:drain_done", "m:before_p_ready", "m:p_ready", "m:before_ds_ready", "m:ds_ready", "m:issued_all"]
-print("cycles relative to compute loop top of tile 0 (CTA 3,0,0; compute warp 0 / MMA warp)")
+names = ["A:loop_top", "A:s_full", "A:exp0_done", "A:p_ready_arrive", "B:loop_top", "B:p_ready", "B:ds_ready_arrive",
+         "B:drain_done", "m:before_p_ready", "m:p_ready", "m:before_ds_ready", "m:ds_ready", "m:issued_all"]
+print("cycles relative to compute loop top of tile 0 (CTA 3,0,0; A warp 0 / B warp 4 / MMA warp)")
 for it in range(8):
     print(f"tile {it}: " + "  ".join(f"{n}={int(t[it, i]) - base}" for i, n in enumerate(names)))
