@@ -20,13 +20,12 @@ int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long widt
 
 constexpr int AB_T = 128;                 // tile edge (queries and keys)
 constexpr int AB_D = 64;
-constexpr int AB_B_WARPS = 4;             // dS warps 0-3:  warp w owns query rows 32*w.., all 128 key columns
-constexpr int AB_A_WARPS = 8;             // P warps 4-11:  warp w owns query rows 32*(w%4).., key columns 64*((w-4)/4)..
-constexpr int AB_TMA_WARP = AB_B_WARPS + AB_A_WARPS, AB_MMA_WARP = AB_TMA_WARP + 1;
-constexpr int AB_THREADS = (AB_MMA_WARP + 1) * 32;
+constexpr int AB_COMPUTE_THREADS = 256;   // warps 0-7: warp w owns query rows 32*(w%4).., key columns 64*(w/4)..
+constexpr int AB_DRAIN_WARP0 = 8;         // warps 8-11: dQ_t TMEM -> shared -> TMA reduce-add, off the compute warps' path
+constexpr int AB_TMA_WARP = 12, AB_MMA_WARP = 13;
+constexpr int AB_THREADS = (AB_MMA_WARP + 1) * 32;    // 448 threads -> 128 registers per thread
 constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB bf16 tile
-constexpr int AB_SMEM = 12 * AB_TILE + 256 + 1024;        // K, V, Q[2], dO[2], P(2), dS(2), dQ staging(2) = 192 KB
-constexpr int AB_SMEM_DROP = 14 * AB_TILE + 256 + 1024;   // + an un-dropped copy of P for the dS warps
+constexpr int AB_SMEM = 12 * AB_TILE + 256 + 1024;   // K, V, Q[2], dO[2], P(2), dS(2), dQ staging(2) = 192 KB
 
 constexpr uint32_t TB_S = 0, TB_DP = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
 
@@ -70,19 +69,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint8_t* sP = smem + 6 * AB_TILE;      // 2 x [128 q][64 keys]
   uint8_t* sdS = smem + 8 * AB_TILE;     // 2 x [128 q][64 keys]
   uint8_t* sStage = smem + 10 * AB_TILE; // 2 x [128 q][32 fp32]
-  uint8_t* sPB = DROP ? smem + 12 * AB_TILE : sP;   // P without dropout (what dS needs); same tile when dropout is off
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (DROP ? 14 : 12) * AB_TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * AB_TILE);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;    // [2]
   uint64_t* q_empty = bars + 3;   // [2]
   uint64_t* s_full = bars + 5;
   uint64_t* dp_full = bars + 6;
-  uint64_t* p_ready = bars + 7;   // 256 arrivals (A warps): P_t in smem, S_t consumed
-  uint64_t* ds_ready = bars + 8;  // 128 arrivals (B warps): dS_t in smem, dP_t consumed
+  uint64_t* p_ready = bars + 7;   // 256 arrivals: P_t in smem, S_t consumed
+  uint64_t* ds_ready = bars + 8;  // 256 arrivals: dS_t in smem, dP_t consumed
   uint64_t* p_free = bars + 9;    // dV_t retired: P buffer reusable
   uint64_t* dq_full = bars + 10;  // dK_t, dQ_t retired: dS buffer reusable, dQ_t readable
   uint64_t* dkv_full = bars + 11;
-  uint64_t* p_read = bars + 12;   // 128 arrivals (B warps): P_t copied to registers, the P tile may be overwritten
+  uint64_t* dq_drained = bars + 12;   // 128 arrivals (drain warps): dQ_t has left TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
@@ -115,12 +113,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(p_ready, AB_A_WARPS * 32);
-    mbar_init(ds_ready, 128);
-    mbar_init(p_read, 128);
+    mbar_init(p_ready, AB_COMPUTE_THREADS);
+    mbar_init(ds_ready, AB_COMPUTE_THREADS);
     mbar_init(p_free, 1);
     mbar_init(dq_full, 1);
     mbar_init(dkv_full, 1);
+    mbar_init(dq_drained, 128);
     fence_mbar_init();
   }
   if (warp == AB_MMA_WARP) {
@@ -203,7 +201,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_wait(p_ready, t & 1);
         AB_STAMP(9);
         tc_fence_after();
-        if (t + 1 < n_iter) {      // S_{t+1} first: the P warps are the longest stage and wait for it
+        if (t + 1 < n_iter) {      // S_{t+1} first: the compute warps start the next tile with it
           mbar_wait(&q_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
           tc_fence_after();
           issue_s(t + 1);
@@ -230,6 +228,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             umma_ss(tmem_base + TB_DK, dS_mn + (uint64_t)(128 * k), dQ_mn + (uint64_t)(128 * k), idesc_t,
                     (t > 0 || k > 0) ? 1u : 0u);
           umma_commit(&q_empty[s]);      // Q_t / dO_t are dead once dK_t retires: the reload for tile t+2 starts now
+        }
+        __syncwarp();
+        if (t > 0) {                     // dQ_{t-1} must have left its TMEM columns
+          mbar_wait(dq_drained, (t - 1) & 1);
+          tc_fence_after();
+        }
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_ss(tmem_base + TB_DQ, (k < 4 ? dS_k0 : dS_k1) + (uint64_t)(2 * (k & 3)), dK_mn + (uint64_t)(128 * k),
@@ -243,225 +248,202 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (elect_one()) umma_commit(dkv_full);
       __syncwarp();
     }
+  } else if (warp >= AB_DRAIN_WARP0) {
+    // ===================== dQ drain warps =====================
+    // dQ_t (128 queries x 64): TMEM -> two swizzled fp32 staging tiles -> TMA reduce-add into the fp32 accumulator in HBM.
+    // Separate warps because this ~750-cycle copy used to sit between the two stages of the compute warps.
+    const int dt = threadIdx.x - AB_DRAIN_WARP0 * 32;      // 0..127 = query row
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int sw = dt & 7;
+    for (int t = 0; t < n_iter; ++t) {
+      mbar_wait(dq_full, t & 1);
+      tc_fence_after();
+      uint32_t r[64];
+      tmem_ld_32x32_at<0>(lane_addr + TB_DQ, r);
+      tmem_ld_32x32_at<32>(lane_addr + TB_DQ + 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_drained);
+      if (dt == 0) tma_wait_group_read<0>();     // the previous reduce has finished reading the staging tiles
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint8_t* rowp = sStage + c * AB_TILE + dt * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) =
+              make_uint4(r[32 * c + 4 * j], r[32 * c + 4 * j + 1], r[32 * c + 4 * j + 2], r[32 * c + 4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (dt == 0) {
+        tma_reduce_add_3d(&tmap_dq, sStage, h * AB_D, (i_begin + t) * AB_T, b);
+        tma_reduce_add_3d(&tmap_dq, sStage + AB_TILE, h * AB_D + 32, (i_begin + t) * AB_T, b);
+        tma_commit_group();
+      }
+    }
+    if (dt == 0) tma_wait_group<0>();
   } else {
     // ===================== compute warps =====================
-    // Warp-specialised by stage (measured with the AB_TRACE build: one group doing both stages serialises ~3750 cycles
-    // per query tile while the tensor pipe needs ~2000):
-    //   A warps 4-11: P_t  = exp2(S_t * c - LSE)              (MUFU-bound)  -> shared memory (bf16)
-    //   B warps 0-3:  dS_t = P_t * (mask * dP_t - D) * scale   + drain of dQ_{t-1} (TMEM -> smem -> TMA reduce-add)
-    // The two groups run one query tile apart; P travels from A to B through the shared-memory tile the dV MMA reads.
-    const bool is_a = warp >= AB_B_WARPS;
-    const int half = is_a ? (warp - AB_B_WARPS) >> 2 : 0;   // A warps: key-column half of S / P; d-column half of the final dK / dV
+    const int half = warp >> 2;                 // key-column half of S / dP, d-column half of dQ / dK / dV
     const int row = (warp & 3) * 32 + lane;     // TMEM lane = query row (S, dP, dQ) or key row (dK, dV)
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int sw = row & 7;
     const float kLog2e = 1.4426950408889634f;
-    const float drop_sc = dropout_scale(p.drop_threshold16);
-    const uint32_t drop_row_stride = (uint32_t)((p.Sk + 1) >> 1);
-    const uint32_t drop_bh = (uint32_t)(((long long)b * p.H + h) * p.Sq);
 
-    if (is_a) {
-      // ---------------------------------------------------------------- A group
-      const int kc0 = k0 + half * 64;             // first key column of this thread
-      float lse_next;
-      {
-        const int qi = i_begin * AB_T + row;
-        lse_next = (n_iter > 0 && qi < p.Sq) ? __ldg(p.lse + ((long long)b * p.H + h) * p.Sq + qi) : INFINITY;
-      }
-      for (int t = 0; t < n_iter; ++t) {
-        const int q0 = (i_begin + t) * AB_T;
-        const int qidx = q0 + row;
-        const float lse2 = lse_next * kLog2e;           // +inf -> P = 0 for padded query rows
-        {                                               // statistics of the next tile: fetched one iteration ahead
-          const int qi = qidx + AB_T;
-          lse_next = (t + 1 < n_iter && qi < p.Sq) ? __ldg(p.lse + ((long long)b * p.H + h) * p.Sq + qi) : INFINITY;
-        }
-        int kmax = p.Sk - 1;
-        if (p.causal) kmax = min(kmax, qidx + shift);
-        const bool need_mask = (k0 + AB_T > p.Sk) || (p.causal && (k0 + AB_T - 1 > q0 + shift));
-        const uint32_t drop_row = (drop_bh + (uint32_t)qidx) * drop_row_stride + (uint32_t)(kc0 >> 1);
+    // per-row statistics of the NEXT query tile are fetched one iteration ahead: a dependent global load at the loop
+    // top costs ~900 cycles per tile (measured with the AB_TRACE build), a fifth of the whole iteration
+    auto load_stats = [&](int t, float& lse_raw, float& dsum_raw) {
+      const int qi = (i_begin + t) * AB_T + row;
+      const bool ok = t < n_iter && qi < p.Sq;
+      const long long idx = ((long long)b * p.H + h) * p.Sq + (ok ? qi : 0);
+      lse_raw = ok ? __ldg(p.lse + idx) : INFINITY;      // +inf -> P = 0 for padded query rows
+      dsum_raw = ok ? __ldg(p.dsum + idx) : 0.f;
+    };
+    float lse_next, dsum_next;
+    load_stats(0, lse_next, dsum_next);
+    for (int t = 0; t < n_iter; ++t) {
+      const int q0 = (i_begin + t) * AB_T;
+      const int qidx = q0 + row;
+      const float lse2 = lse_next * kLog2e;
+      const float dsum = dsum_next;
+      load_stats(t + 1, lse_next, dsum_next);
+      int kmax = p.Sk - 1;
+      if (p.causal) kmax = min(kmax, qidx + shift);
+      const bool need_mask = (k0 + AB_T > p.Sk) || (p.causal && (k0 + AB_T - 1 > q0 + shift));
+      const int kbase = k0 + half * 64;
+
+      // ---------------- stage A: P_t ----------------
+      // P is kept as packed bf16 pairs (what the dV MMA sees); under dropout the sign bit of each half carries
+      // "dropped in the forward pass" (P >= 0, so the bit is free) and pd holds the dropped, rescaled copy for dV.
+      uint32_t pk[32];
+      uint32_t pd[DROP ? 32 : 1];
+      // dropout pair index of (query row, key k) = drop_row + k / 2, exactly as in the forward kernel
+      const uint32_t drop_row = (uint32_t)((((long long)b * p.H + h) * p.Sq + qidx) * ((p.Sk + 1) >> 1)) +
+                                (uint32_t)(kbase >> 1);
+      const float drop_sc = dropout_scale(p.drop_threshold16);
 #ifdef AB_TRACE
-        const bool trace_on = p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 &&
-                              threadIdx.x == AB_B_WARPS * 32;
+      const bool trace_on = p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
 #endif
-        AB_STAMP(0);
-        mbar_wait(s_full, t & 1);
-        AB_STAMP(1);
-        tc_fence_after();
-        uint32_t rs[64];
-        tmem_ld_32x32_at<0>(lane_addr + TB_S + half * 64, rs);
-        tmem_ld_32x32_at<32>(lane_addr + TB_S + half * 64 + 32, rs);
+      AB_STAMP(0);
+      mbar_wait(s_full, t & 1);
+      AB_STAMP(1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rs[32];
+        tmem_ld_32x32(lane_addr + TB_S + half * 64 + c * 32, rs);
         tmem_ld_wait();
-        float pv[64];
-        if (need_mask) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e) {
-            float v = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
-            if (kc0 + e > kmax) v = 0.f;
-            pv[e] = v;
+        for (int e = 0; e < 32; e += 2) {
+          float v0 = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
+          float v1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2));
+          if (need_mask) {
+            if (kbase + c * 32 + e > kmax) v0 = 0.f;
+            if (kbase + c * 32 + e + 1 > kmax) v1 = 0.f;
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 64; ++e) pv[e] = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
+          uint32_t w = pack_bf16(v0, v1);
+          if (DROP) {
+            const uint32_t hsh = dropout_hash(p.drop_seed, drop_row + (uint32_t)((c * 32 + e) >> 1));
+            const bool keep0 = (hsh & 0xFFFFu) >= p.drop_threshold16, keep1 = (hsh >> 16) >= p.drop_threshold16;
+            pd[DROP ? c * 16 + (e >> 1) : 0] = pack_bf16(keep0 ? v0 * drop_sc : 0.f, keep1 ? v1 * drop_sc : 0.f);
+            w |= (keep0 ? 0u : 0x8000u) | (keep1 ? 0u : 0x80000000u);
+          }
+          pk[c * 16 + (e >> 1)] = w;
         }
-        AB_STAMP(2);
-        if (t > 0) {
-          mbar_wait(p_free, (t - 1) & 1);     // dV_{t-1} no longer reads the P tile
-          mbar_wait(p_read, (t - 1) & 1);     // the B warps have copied P_{t-1} out of it
-        }
+      }
+      AB_STAMP(2);
+      if (t > 0) mbar_wait(p_free, (t - 1) & 1);      // dV_{t-1} no longer reads the P buffer
+      {
         uint8_t* prow = sP + half * AB_TILE + row * 128;
-        uint8_t* pbrow = sPB + half * AB_TILE + row * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (DROP) {      // the dS warps need P itself, the dV MMA the dropped probabilities
-            *reinterpret_cast<uint4*>(pbrow + ((j ^ sw) << 4)) =
-                make_uint4(pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
-                           pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
-#pragma unroll
-            for (int e = 0; e < 8; e += 2)
-              dropout_pair(p.drop_seed, drop_row + (uint32_t)((8 * j + e) >> 1), p.drop_threshold16, drop_sc,
-                           pv[8 * j + e], pv[8 * j + e + 1]);
-          }
-          *reinterpret_cast<uint4*>(prow + ((j ^ sw) << 4)) =
-              make_uint4(pack_bf16(pv[8 * j], pv[8 * j + 1]), pack_bf16(pv[8 * j + 2], pv[8 * j + 3]),
-                         pack_bf16(pv[8 * j + 4], pv[8 * j + 5]), pack_bf16(pv[8 * j + 6], pv[8 * j + 7]));
+          if (DROP)
+            *reinterpret_cast<uint4*>(prow + ((j ^ sw) << 4)) =
+                make_uint4(pd[DROP ? 4 * j : 0], pd[DROP ? 4 * j + 1 : 0], pd[DROP ? 4 * j + 2 : 0], pd[DROP ? 4 * j + 3 : 0]);
+          else
+            *reinterpret_cast<uint4*>(prow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
-        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        tc_fence_before();
-        mbar_arrive(p_ready);
-        AB_STAMP(3);
       }
-    } else {
-      // ---------------------------------------------------------------- B group
-      const int bt = threadIdx.x;                 // 0..127
-      float dsum_next;
+      fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      AB_STAMP(3);
+
+      if (t > 0) mbar_wait(dq_full, (t - 1) & 1);     // dK_{t-1} / dQ_{t-1} no longer read the dS buffer
+      AB_STAMP(7);
+
+      // ---------------- stage B: dS_t ----------------
+      const f32x2 ndsum2 = f2_splat(-dsum), scale2 = f2_splat(p.scale);
+      AB_STAMP(4);
+      mbar_wait(dp_full, t & 1);
+      AB_STAMP(5);
+      tc_fence_after();
       {
-        const int qi = i_begin * AB_T + row;
-        dsum_next = (n_iter > 0 && qi < p.Sq) ? __ldg(p.dsum + ((long long)b * p.H + h) * p.Sq + qi) : 0.f;
-      }
-      auto drain_dq = [&](int t) {
-        // dQ_t (64 columns of this row): TMEM -> two swizzled fp32 staging tiles -> TMA reduce-add into HBM
-        if (bt == 0) tma_wait_group_read<0>();     // the previous reduce has finished reading the staging tiles
-        named_bar_sync(1, 128);
-#pragma unroll 1
+        uint8_t* drow = sdS + half * AB_TILE + row * 128;
+#pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(lane_addr + TB_DQ + c * 32, r);
-          tmem_ld_wait();
-          uint8_t* rowp = sStage + c * AB_TILE + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        named_bar_sync(1, 128);
-        if (bt == 0) {
-          tma_reduce_add_3d(&tmap_dq, sStage, h * AB_D, (i_begin + t) * AB_T, b);
-          tma_reduce_add_3d(&tmap_dq, sStage + AB_TILE, h * AB_D + 32, (i_begin + t) * AB_T, b);
-          tma_commit_group();
-        }
-      };
-      for (int t = 0; t < n_iter; ++t) {
-        const int qidx = (i_begin + t) * AB_T + row;
-        const float dsum = dsum_next;
-        {
-          const int qi = qidx + AB_T;
-          dsum_next = (t + 1 < n_iter && qi < p.Sq) ? __ldg(p.dsum + ((long long)b * p.H + h) * p.Sq + qi) : 0.f;
-        }
-        const uint32_t drop_row = (drop_bh + (uint32_t)qidx) * drop_row_stride + (uint32_t)(k0 >> 1);
-#ifdef AB_TRACE
-        const bool trace_on = p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && bt == 0;
-#endif
-        // ---- P_t (bf16) from the shared-memory tile the A warps filled
-        AB_STAMP(4);
-        mbar_wait(p_ready, t & 1);
-        AB_STAMP(5);
-        uint4 pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          pk[j] = *reinterpret_cast<const uint4*>(sPB + (j >> 3) * AB_TILE + row * 128 + (((j & 7) ^ sw) << 4));
-        mbar_arrive(p_read);
-        // ---- dQ of the previous tile leaves; this also guarantees dK_{t-1} / dQ_{t-1} no longer read the dS tile
-        if (t > 0) {
-          mbar_wait(dq_full, (t - 1) & 1);
-          tc_fence_after();
-          drain_dq(t - 1);
-        }
-        AB_STAMP(7);
-        // ---- dS_t
-        mbar_wait(dp_full, t & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {          // 32 key columns at a time (register budget: 128 / thread)
           uint32_t rp[32];
-          tmem_ld_32x32(lane_addr + TB_DP + c * 32, rp);
+          tmem_ld_32x32(lane_addr + TB_DP + half * 64 + c * 32, rp);
           tmem_ld_wait();
-          uint8_t* drow = sdS + (c >> 1) * AB_TILE + row * 128;
+          float dsv[32];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 pq = pk[c * 4 + j];
-            const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
-            float d[8];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              float g0 = __uint_as_float(rp[8 * j + e]), g1 = __uint_as_float(rp[8 * j + e + 1]);
-              if (DROP)
-                dropout_pair(p.drop_seed, drop_row + (uint32_t)((c * 32 + 8 * j + e) >> 1), p.drop_threshold16,
-                             drop_sc, g0, g1);
-              d[e] = bf16_lo(pw[e >> 1]) * (g0 - dsum) * p.scale;
-              d[e + 1] = bf16_hi(pw[e >> 1]) * (g1 - dsum) * p.scale;
+          for (int e = 0; e < 32; e += 2) {      // dS = P * (mask * dP - D) * scale, on packed fp32 pairs
+            uint32_t w = pk[c * 16 + (e >> 1)];
+            f32x2 g = f2_pack(__uint_as_float(rp[e]), __uint_as_float(rp[e + 1]));
+            if (DROP) {
+              g = f2_mul(g, f2_pack((w & 0x8000u) ? 0.f : drop_sc, (w & 0x80000000u) ? 0.f : drop_sc));
+              w &= 0x7FFF7FFFu;
             }
-            *reinterpret_cast<uint4*>(drow + ((((c & 1) * 4 + j) ^ sw) << 4)) =
-                make_uint4(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]), pack_bf16(d[4], d[5]), pack_bf16(d[6], d[7]));
+            const f32x2 ps = f2_mul(f2_pack(bf16_lo(w), bf16_hi(w)), scale2);
+            f2_unpack(f2_mul(f2_add(g, ndsum2), ps), dsv[e], dsv[e + 1]);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int piece = (c * 4 + jj) ^ sw;
+            *reinterpret_cast<uint4*>(drow + (piece << 4)) =
+                make_uint4(pack_bf16(dsv[8 * jj], dsv[8 * jj + 1]), pack_bf16(dsv[8 * jj + 2], dsv[8 * jj + 3]),
+                           pack_bf16(dsv[8 * jj + 4], dsv[8 * jj + 5]), pack_bf16(dsv[8 * jj + 6], dsv[8 * jj + 7]));
           }
         }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(ds_ready);
-        AB_STAMP(6);
       }
-      if (n_iter > 0) {
-        mbar_wait(dq_full, (n_iter - 1) & 1);
-        tc_fence_after();
-        drain_dq(n_iter - 1);
-      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+      AB_STAMP(6);
     }
     if (n_iter > 0) {
       mbar_wait(dkv_full, 0);
       tc_fence_after();
     }
-    if (is_a) {
-      // ---- final: dK, dV (rows = keys of this tile; this thread owns d columns [32*half, 32*half+32)) -> bf16 -> global
-      const int kidx = k0 + row;
-      const bool k_ok = kidx < p.Sk;
-      bf16* dkrow = p.dk + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dk + p.dk_col0 + h * AB_D + half * 32;
-      bf16* dvrow = p.dv + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dv + p.dv_col0 + h * AB_D + half * 32;
-  #pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
-        bf16* orow = which == 0 ? dvrow : dkrow;
-        uint32_t r[32];
-        if (n_iter > 0) {
-          tmem_ld_32x32(lane_addr + (which == 0 ? TB_DV : TB_DK) + half * 32, r);
-          tmem_ld_wait();
-        } else {
-  #pragma unroll
-          for (int e = 0; e < 32; ++e) r[e] = 0u;
-        }
-        if (k_ok) {
-  #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(r[8 * v4 + 0]), __uint_as_float(r[8 * v4 + 1]));
-            o.y = pack_bf16(__uint_as_float(r[8 * v4 + 2]), __uint_as_float(r[8 * v4 + 3]));
-            o.z = pack_bf16(__uint_as_float(r[8 * v4 + 4]), __uint_as_float(r[8 * v4 + 5]));
-            o.w = pack_bf16(__uint_as_float(r[8 * v4 + 6]), __uint_as_float(r[8 * v4 + 7]));
-            *reinterpret_cast<uint4*>(orow + v4 * 8) = o;
-          }
+    // ---- final: dK, dV (rows = keys of this tile; this thread owns d columns [32*half, 32*half+32)) -> bf16 -> global
+    const int kidx = k0 + row;
+    const bool k_ok = kidx < p.Sk;
+    bf16* dkrow = p.dk + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dk + p.dk_col0 + h * AB_D + half * 32;
+    bf16* dvrow = p.dv + ((long long)b * p.Sk + (k_ok ? kidx : 0)) * p.ld_dv + p.dv_col0 + h * AB_D + half * 32;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      bf16* orow = which == 0 ? dvrow : dkrow;
+      uint32_t r[32];
+      if (n_iter > 0) {
+        tmem_ld_32x32(lane_addr + (which == 0 ? TB_DV : TB_DK) + half * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = 0u;
+      }
+      if (k_ok) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(r[8 * v4 + 0]), __uint_as_float(r[8 * v4 + 1]));
+          o.y = pack_bf16(__uint_as_float(r[8 * v4 + 2]), __uint_as_float(r[8 * v4 + 3]));
+          o.z = pack_bf16(__uint_as_float(r[8 * v4 + 4]), __uint_as_float(r[8 * v4 + 5]));
+          o.w = pack_bf16(__uint_as_float(r[8 * v4 + 6]), __uint_as_float(r[8 * v4 + 7]));
+          *reinterpret_cast<uint4*>(orow + v4 * 8) = o;
         }
       }
     }
-    if (threadIdx.x == 0) tma_wait_group<0>();
   }
 
   tc_fence_before();
@@ -618,12 +600,12 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
   if (!configured) {
     e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_DROP);
+      e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attention_bwd)");
     configured = true;
   }
   dim3 grid((Sk + AB_T - 1) / AB_T, H, B);
-  if (p.drop_threshold16 != 0u) attention_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM_DROP, s>>>(tq, tk, tv, tdo, tdq, p);
+  if (p.drop_threshold16 != 0u) attention_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
   else attention_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
   B200_CHECK_LAUNCH("attention_bwd");
 

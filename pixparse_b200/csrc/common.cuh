@@ -316,6 +316,61 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, E, cdf);
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) ------------------------------------------------
+// A 3-register FFMA issues every second cycle per SM sub-partition; the f32x2 forms do two lanes' worth per issue, so
+// the fp32-heavy epilogues (bias, GELU, GELU', dropout scaling) cost half the fma-pipe slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// pair forms of gelu_erf / gelu_erf_grad (same polynomial; the clamp moves to x^2 <= 36, one FMNMX per lane:
+// beyond |x| = 6 the tanh argument keeps growing linearly with the positive slope p(36), so tanh -> +-1 as it must)
+__device__ __forceinline__ f32x2 gelu_tanh2(f32x2 x, f32x2& x2c) {
+  float a, b;
+  f2_unpack(f2_mul(x, x), a, b);
+  x2c = f2_pack(fminf(a, 36.0f), fminf(b, 36.0f));
+  f32x2 p = f2_fma(x2c, f2_splat(-3.47437544e-04f), f2_splat(3.69593885e-02f));
+  p = f2_fma(x2c, p, f2_splat(7.97600733e-01f));
+  f2_unpack(f2_mul(x, p), a, b);
+  return f2_pack(tanh_approx(a), tanh_approx(b));
+}
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  f32x2 x2c;
+  const f32x2 t = gelu_tanh2(x, x2c);
+  const f32x2 hx = f2_mul(x, f2_splat(0.5f));
+  return f2_fma(hx, t, hx);
+}
+__device__ __forceinline__ f32x2 gelu_erf_grad2(f32x2 x) {
+  f32x2 x2c;
+  const f32x2 t = gelu_tanh2(x, x2c);
+  const f32x2 cdf = f2_fma(t, f2_splat(0.5f), f2_splat(0.5f));
+  float a, b;
+  f2_unpack(f2_mul(x2c, f2_splat(-0.72134752044448170f)), a, b);      // exp(-x^2 / 2); 1.5e-8 at the clamp
+  const f32x2 E = f2_pack(ex2_approx(a), ex2_approx(b));
+  return f2_fma(f2_mul(x, f2_splat(0.3989422804014327f)), E, cdf);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -117,6 +117,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
         if (col + e < p.N) b4[e] = __ldg(p.bias + col + e);
     }
   }
+  const f32x2 b01 = f2_pack(b4[0], b4[1]), b23 = f2_pack(b4[2], b4[3]);
   const long long out_off = (long long)row0 * p.ldo + col;
   const long long out_step = 16 * p.ldo;
   bf16* o16 = reinterpret_cast<bf16*>(p.out) + out_off;
@@ -127,20 +128,28 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
     const int rt = rt0 + 16 * i;
     if (INTERIOR || row0 + 16 * i < p.M) {
       const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
-      float v[4] = {__uint_as_float(raw.x) + b4[0], __uint_as_float(raw.y) + b4[1], __uint_as_float(raw.z) + b4[2],
-                    __uint_as_float(raw.w) + b4[3]};
-      float dm[4] = {1.f, 1.f, 1.f, 1.f};     // dropout multipliers of the 4 columns (N is even when dropout is on)
-      if ((EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16) &&
-          p.drop_threshold16 != 0u) {
+      // fp32 pairs: the arithmetic below runs on the packed FFMA2 / FMUL2 / FADD2 forms (half the fma-pipe issue slots)
+      f32x2 v01 = f2_add(f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y)), b01);
+      f32x2 v23 = f2_add(f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w)), b23);
+      f32x2 dm01 = 0ull, dm23 = 0ull;         // dropout multipliers of the 4 columns (N is even when dropout is on)
+      const bool drop_on = (EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16) &&
+                           p.drop_threshold16 != 0u;
+      if (drop_on) {
         const uint32_t pair = (uint32_t)(((long long)(row0 + 16 * i) * p.N + col) >> 1);
         const float sc = dropout_scale(p.drop_threshold16);
-        dropout_pair(p.drop_seed, pair, p.drop_threshold16, sc, dm[0], dm[1]);
-        dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, sc, dm[2], dm[3]);
+        float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
+        dropout_pair(p.drop_seed, pair, p.drop_threshold16, sc, d0, d1);
+        dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, sc, d2, d3);
+        dm01 = f2_pack(d0, d1);
+        dm23 = f2_pack(d2, d3);
         if (EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_DGELU_BF16) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] *= dm[e];
+          v01 = f2_mul(v01, dm01);
+          v23 = f2_mul(v23, dm23);
         }
       }
+      float v[4];
+      f2_unpack(v01, v[0], v[1]);
+      f2_unpack(v23, v[2], v[3]);
       if (EPI == B200_EPI_STORE_BF16) {
         if (full4) {
           *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
@@ -151,8 +160,15 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
       } else if (EPI == B200_EPI_GELU_BF16) {
         // out2 = pre-activation h (bf16); out = gelu(h) evaluated on the ROUNDED h (what autocast feeds nn.GELU)
         const uint32_t h01 = pack_bf16(v[0], v[1]), h23 = pack_bf16(v[2], v[3]);
-        const float g0 = gelu_erf(bf16_lo(h01)) * dm[0], g1 = gelu_erf(bf16_hi(h01)) * dm[1];
-        const float g2 = gelu_erf(bf16_lo(h23)) * dm[2], g3 = gelu_erf(bf16_hi(h23)) * dm[3];
+        f32x2 g01 = gelu_erf2(f2_pack(bf16_lo(h01), bf16_hi(h01)));
+        f32x2 g23 = gelu_erf2(f2_pack(bf16_lo(h23), bf16_hi(h23)));
+        if (drop_on) {
+          g01 = f2_mul(g01, dm01);
+          g23 = f2_mul(g23, dm23);
+        }
+        float g0, g1, g2, g3;
+        f2_unpack(g01, g0, g1);
+        f2_unpack(g23, g2, g3);
         if (full4) {
           *reinterpret_cast<uint2*>(o2) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, g3));
@@ -169,7 +185,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
         // out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
         if (full4) {
           const float4 rv = aux.f[i];
-          *reinterpret_cast<float4*>(o32) = make_float4(rv.x + v[0], rv.y + v[1], rv.z + v[2], rv.w + v[3]);
+          float o0, o1, o2_, o3;
+          f2_unpack(f2_add(f2_pack(rv.x, rv.y), v01), o0, o1);
+          f2_unpack(f2_add(f2_pack(rv.z, rv.w), v23), o2_, o3);
+          *reinterpret_cast<float4*>(o32) = make_float4(o0, o1, o2_, o3);
         } else {
           const float* a = reinterpret_cast<const float*>(p.aux) + (long long)(row0 + 16 * i) * p.ld_aux + col;
           for (int e = 0; e < 4; ++e)
@@ -179,9 +198,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
         // out = acc * gelu'(h), h = saved bf16 pre-activation
         if (full4) {
           const uint2 hv = aux.h[i];
-          *reinterpret_cast<uint2*>(o16) =
-              make_uint2(pack_bf16(v[0] * gelu_erf_grad(bf16_lo(hv.x)), v[1] * gelu_erf_grad(bf16_hi(hv.x))),
-                         pack_bf16(v[2] * gelu_erf_grad(bf16_lo(hv.y)), v[3] * gelu_erf_grad(bf16_hi(hv.y))));
+          float o0, o1, o2_, o3;
+          f2_unpack(f2_mul(v01, gelu_erf_grad2(f2_pack(bf16_lo(hv.x), bf16_hi(hv.x)))), o0, o1);
+          f2_unpack(f2_mul(v23, gelu_erf_grad2(f2_pack(bf16_lo(hv.y), bf16_hi(hv.y)))), o2_, o3);
+          *reinterpret_cast<uint2*>(o16) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2_, o3));
         } else {
           const bf16* a = reinterpret_cast<const bf16*>(p.aux) + (long long)(row0 + 16 * i) * p.ld_aux + col;
           for (int e = 0; e < 4; ++e)
