@@ -268,11 +268,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       named_bar_sync(1, 128);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint8_t* rowp = sStage + c * AB_TILE + dt * 128;
+        const uint32_t rowp = smem_u32(sStage) + c * AB_TILE + dt * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) =
-              make_uint4(r[32 * c + 4 * j], r[32 * c + 4 * j + 1], r[32 * c + 4 * j + 2], r[32 * c + 4 * j + 3]);
+          sts128(rowp + ((j ^ sw) << 4), r[32 * c + 4 * j], r[32 * c + 4 * j + 1], r[32 * c + 4 * j + 2], r[32 * c + 4 * j + 3]);
       }
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
@@ -355,14 +354,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       AB_STAMP(2);
       if (t > 0) mbar_wait(p_free, (t - 1) & 1);      // dV_{t-1} no longer reads the P buffer
       {
-        uint8_t* prow = sP + half * AB_TILE + row * 128;
+        const uint32_t prow = smem_u32(sP) + half * AB_TILE + row * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (DROP)
-            *reinterpret_cast<uint4*>(prow + ((j ^ sw) << 4)) =
-                make_uint4(pd[DROP ? 4 * j : 0], pd[DROP ? 4 * j + 1 : 0], pd[DROP ? 4 * j + 2 : 0], pd[DROP ? 4 * j + 3 : 0]);
+            sts128(prow + ((j ^ sw) << 4), pd[DROP ? 4 * j : 0], pd[DROP ? 4 * j + 1 : 0], pd[DROP ? 4 * j + 2 : 0],
+                   pd[DROP ? 4 * j + 3 : 0]);
           else
-            *reinterpret_cast<uint4*>(prow + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            sts128(prow + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
       fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -380,7 +379,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       AB_STAMP(5);
       tc_fence_after();
       {
-        uint8_t* drow = sdS + half * AB_TILE + row * 128;
+        const uint32_t drow = smem_u32(sdS) + half * AB_TILE + row * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t rp[32];
@@ -401,9 +400,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int piece = (c * 4 + jj) ^ sw;
-            *reinterpret_cast<uint4*>(drow + (piece << 4)) =
-                make_uint4(pack_bf16(dsv[8 * jj], dsv[8 * jj + 1]), pack_bf16(dsv[8 * jj + 2], dsv[8 * jj + 3]),
-                           pack_bf16(dsv[8 * jj + 4], dsv[8 * jj + 5]), pack_bf16(dsv[8 * jj + 6], dsv[8 * jj + 7]));
+            sts128(drow + (piece << 4), pack_bf16(dsv[8 * jj], dsv[8 * jj + 1]), pack_bf16(dsv[8 * jj + 2], dsv[8 * jj + 3]),
+                   pack_bf16(dsv[8 * jj + 4], dsv[8 * jj + 5]), pack_bf16(dsv[8 * jj + 6], dsv[8 * jj + 7]));
           }
         }
       }

@@ -316,6 +316,19 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, E, cdf);
 }
 
+// ---- explicit shared-space 16-byte accesses -----------------------------------------------------------
+// Pointers derived from the dynamic shared-memory base are generic to the compiler: it emits LD.E / ST.E, which hold
+// their registers on the long scoreboard (ncu: the GELU epilogue spent 40 % of its stall samples there). These
+// take the 32-bit shared address (smem_u32) instead.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) ------------------------------------------------
 // A 3-register FFMA issues every second cycle per SM sub-partition; the f32x2 forms do two lanes' worth per issue, so
 // the fp32-heavy epilogues (bias, GELU, GELU', dropout scaling) cost half the fma-pipe slots.

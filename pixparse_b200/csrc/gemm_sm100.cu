@@ -78,10 +78,12 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_t
 struct EpiAux {
   float4 f[8];
   uint2 h[8];
+  float4 bias;      // bias of this thread's 4 columns, fetched with the aux rows ahead of the staging barriers
 };
 template <int EPI>
 __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, int row0, int col, EpiAux& aux) {
   if (col + 3 >= p.N) return;      // partial column group: handled element-wise in epilogue_rows
+  if (p.bias != nullptr) aux.bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
   if (EPI == B200_EPI_RESID_F32) {
     const float* a = reinterpret_cast<const float*>(p.aux) + (long long)row0 * p.ld_aux + col;
 #pragma unroll
@@ -101,7 +103,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, int row0,
 }
 
 template <int EPI, bool INTERIOR>
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t* buf, int et, int row0, int col,
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_s, int et, int row0, int col,
                                               const EpiAux& aux) {
   const int cq = et & 7;
   const int rt0 = et >> 3;
@@ -110,8 +112,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
   float b4[4] = {0.f, 0.f, 0.f, 0.f};
   if (p.bias != nullptr) {
     if (full4) {
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      b4[0] = bv.x; b4[1] = bv.y; b4[2] = bv.z; b4[3] = bv.w;
+      b4[0] = aux.bias.x; b4[1] = aux.bias.y; b4[2] = aux.bias.z; b4[3] = aux.bias.w;
     } else {
       for (int e = 0; e < 4; ++e)
         if (col + e < p.N) b4[e] = __ldg(p.bias + col + e);
@@ -127,7 +128,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const uint8_t
   for (int i = 0; i < 8; ++i) {
     const int rt = rt0 + 16 * i;
     if (INTERIOR || row0 + 16 * i < p.M) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(buf + rt * 128 + ((cq ^ (rt & 7)) << 4));
+      const uint4 raw = lds128(buf_s + rt * 128 + ((cq ^ (rt & 7)) << 4));
       // fp32 pairs: the arithmetic below runs on the packed FFMA2 / FMUL2 / FADD2 forms (half the fma-pipe issue slots)
       f32x2 v01 = f2_add(f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y)), b01);
       f32x2 v23 = f2_add(f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w)), b23);
@@ -363,6 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int row_in_tile = ew * 32 + lane;    // accumulator row owned in phase 1
     const uint32_t bar_id = 1 + grp;
     uint8_t* buf = epi_buf + grp * EPI_BUF_BYTES;
+    const uint32_t buf_s = smem_u32(buf);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -379,7 +381,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int c = grp; c < BN / EPI_COLS; c += 2) {
         const int col = n_tile * BN + c * EPI_COLS + (et & 7) * 4;
         EpiAux aux;
-        if (EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_DGELU_BF16) epilogue_prefetch<EPI>(p, row0, col, aux);
+        if (EPI != B200_EPI_REDUCE_F32) epilogue_prefetch<EPI>(p, row0, col, aux);
         tmem_ld_wait();
         if (c + 2 >= BN / EPI_COLS) {
           // this thread's last TMEM read of the accumulator stage: hand it back to the MMA warp
@@ -393,13 +395,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         named_bar_sync(bar_id, 128);
         // phase 1: row-per-thread -> swizzled staging tile (conflict-free 16-byte stores)
         {
-          uint8_t* rowp = buf + row_in_tile * 128;
+          const uint32_t rowp = buf_s + row_in_tile * 128;
           const int sw = row_in_tile & 7;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = v;
-          }
+          for (int j = 0; j < 8; ++j) sts128(rowp + ((j ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         }
         // r is dead: start the TMEM load of this group's next chunk so it overlaps the barrier + phase 2
         if (c + 2 < BN / EPI_COLS) tmem_ld_32x32(taddr + (c + 2) * EPI_COLS, r);
@@ -413,8 +412,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         } else {
           named_bar_sync(bar_id, 128);
           // phase 2: coalesced pass. thread -> (row = et/8 + 16*i, 4 columns at (et%8)*4)
-          if (interior) epilogue_rows<EPI, true>(p, buf, et, row0, col, aux);
-          else epilogue_rows<EPI, false>(p, buf, et, row0, col, aux);
+          if (interior) epilogue_rows<EPI, true>(p, buf_s, et, row0, col, aux);
+          else epilogue_rows<EPI, false>(p, buf_s, et, row0, col, aux);
         }
       }
       if (++acc == 2) {
