@@ -38,7 +38,7 @@ int check_cuda(cudaError_t e, const char* what);
 int num_sms();
 
 // TMA descriptor encode (host). dims/strides innermost-first; strides in bytes for dims 1..rank-1.
-enum TmaSwizzle { TMA_SWIZZLE_NONE = 0, TMA_SWIZZLE_128B = 3 };
+enum TmaSwizzle { TMA_SWIZZLE_NONE = 0, TMA_SWIZZLE_64B = 2, TMA_SWIZZLE_128B = 3 };
 enum TmaDtype { TMA_BF16 = 0, TMA_F32 = 1 };
 int make_tmap(CUtensorMap* out, const void* base, TmaDtype dt, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz);

@@ -42,6 +42,8 @@ struct GemmParams {
   // dropout fused into the epilogue (threshold 0 = off): RESID drops (acc + bias) before the residual add,
   // GELU drops the activation (not the saved pre-activation), DGELU masks the incoming gradient
   uint32_t drop_threshold16, drop_seed;
+  // STORE_BF16 / GELU_BF16: outputs leave through TMA stores (needs 16-byte aligned base and row pitch)
+  int tma_epi;
 };
 
 // debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
@@ -54,7 +56,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (256 or 512 columns: powers of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 256 + 1024 /* bias */ + 1024 /* align */;
 };
 
 __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& n_tile, int& split) {
@@ -226,7 +228,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+            const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -239,6 +242,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* epi_bias = reinterpret_cast<float*>(epi_buf + 2 * EPI_BUF_BYTES + 256);   // 2 groups x 128 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -246,7 +250,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    if (EPI == B200_EPI_REDUCE_F32) prefetch_tmap(&tmap_out);
+    if (EPI == B200_EPI_REDUCE_F32 || EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_GELU_BF16) prefetch_tmap(&tmap_out);
+    if (EPI == B200_EPI_GELU_BF16) prefetch_tmap(&tmap_out2);
   }
   if (warp == 11 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -367,6 +372,110 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const uint32_t buf_s = smem_u32(buf);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if ((EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_GELU_BF16) && p.tma_epi) {
+      // ---- bf16 outputs through TMA stores: the math runs in the accumulator's own row-per-thread layout, the packed
+      // result is staged once in the swizzled layout the tensor map expects and leaves as one bulk store per round.
+      // No second pass over shared memory, no per-thread global stores (ncu on the two-pass version: the epilogue
+      // warps, not the tensor pipe, bounded every K = 768 GEMM; 2/3 of their stall samples were scoreboard waits on
+      // the staging reads and on registers held by in-flight STGs).
+      //   STORE: rounds of 64 columns (128-byte rows, SWIZZLE_128B), GELU: rounds of 32 columns, two 64-byte-row tiles
+      //   (pre-activation and activation, SWIZZLE_64B).
+      constexpr int CW = (EPI == B200_EPI_STORE_BF16) ? 64 : 32;
+      constexpr int ROUNDS = BN / CW / 2;            // per group and tile; the groups take alternating rounds
+      float* sbias = epi_bias + grp * 128;           // bias of this group's BN / 2 columns, [round][CW]
+      const uint32_t sbias_s = smem_u32(sbias);
+      const int swz = (EPI == B200_EPI_STORE_BF16) ? (row_in_tile & 7) : ((row_in_tile >> 1) & 3);
+      const uint32_t rowp = buf_s + row_in_tile * (CW * 2);
+      const float drop_sc = dropout_scale(p.drop_threshold16);
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int m_tile, n_tile, split;
+        decode_work(p, w, m_tile, n_tile, split);
+        if (p.bias != nullptr) {
+          if (et < BN / 2) {
+            const int col = n_tile * BN + (grp + 2 * (et / CW)) * CW + (et % CW);
+            sbias[et] = col < p.N ? __ldg(p.bias + col) : 0.f;
+          }
+          named_bar_sync(bar_id, 128);     // (every thread of the group is past the previous tile's bias reads: they
+        }                                  //  precede that tile's last staging barrier)
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+        const int grow = m_tile * BM + row_in_tile;
+#pragma unroll 1
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+          const int cc = (grp + 2 * rd) * CW;        // first column of the round inside the tile
+          uint32_t r[CW];
+          tmem_ld_32x32_at<0>(taddr + cc, r);
+          if (CW == 64) tmem_ld_32x32_at<(CW == 64 ? 32 : 0)>(taddr + cc + 32, r);
+          tmem_ld_wait();
+          if (rd == ROUNDS - 1) {          // last TMEM read of this accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          uint32_t o[CW / 2];
+          uint32_t o2[EPI == B200_EPI_GELU_BF16 ? CW / 2 : 1];
+#pragma unroll
+          for (int q = 0; q < CW / 4; ++q) {
+            f32x2 v01 = f2_pack(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]));
+            f32x2 v23 = f2_pack(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            if (p.bias != nullptr) {
+              const uint4 bq = lds128(sbias_s + (rd * CW + 4 * q) * 4);      // same address in every lane: broadcast
+              v01 = f2_add(v01, f2_pack(__uint_as_float(bq.x), __uint_as_float(bq.y)));
+              v23 = f2_add(v23, f2_pack(__uint_as_float(bq.z), __uint_as_float(bq.w)));
+            }
+            float v0, v1, v2, v3;
+            f2_unpack(v01, v0, v1);
+            f2_unpack(v23, v2, v3);
+            const uint32_t h01 = pack_bf16(v0, v1), h23 = pack_bf16(v2, v3);
+            if (EPI == B200_EPI_STORE_BF16) {
+              o[2 * q] = h01;
+              o[2 * q + 1] = h23;
+            } else {
+              // out2 = pre-activation h (bf16); out = gelu(h) evaluated on the ROUNDED h (what autocast feeds nn.GELU)
+              o2[EPI == B200_EPI_GELU_BF16 ? 2 * q : 0] = h01;
+              o2[EPI == B200_EPI_GELU_BF16 ? 2 * q + 1 : 0] = h23;
+              f32x2 g01 = gelu_erf2(f2_pack(bf16_lo(h01), bf16_hi(h01)));
+              f32x2 g23 = gelu_erf2(f2_pack(bf16_lo(h23), bf16_hi(h23)));
+              if (p.drop_threshold16 != 0u) {
+                const uint32_t pair = (uint32_t)(((long long)grow * p.N + (n_tile * BN + cc + 4 * q)) >> 1);
+                float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
+                dropout_pair(p.drop_seed, pair, p.drop_threshold16, drop_sc, d0, d1);
+                dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, drop_sc, d2, d3);
+                g01 = f2_mul(g01, f2_pack(d0, d1));
+                g23 = f2_mul(g23, f2_pack(d2, d3));
+              }
+              f2_unpack(g01, v0, v1);
+              f2_unpack(g23, v2, v3);
+              o[2 * q] = pack_bf16(v0, v1);
+              o[2 * q + 1] = pack_bf16(v2, v3);
+            }
+          }
+          // the staging tile(s) must be free: the previous round's bulk store has finished reading them
+          if (et == 0) tma_wait_group_read<0>();
+          named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) {
+            sts128(rowp + ((j ^ swz) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            if (EPI == B200_EPI_GELU_BF16)
+              sts128(rowp + EPI_BUF_BYTES / 2 + ((j ^ swz) << 4), o2[EPI == B200_EPI_GELU_BF16 ? 4 * j : 0],
+                     o2[EPI == B200_EPI_GELU_BF16 ? 4 * j + 1 : 0], o2[EPI == B200_EPI_GELU_BF16 ? 4 * j + 2 : 0],
+                     o2[EPI == B200_EPI_GELU_BF16 ? 4 * j + 3 : 0]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (et == 0 && n_tile * BN + cc < p.N) {
+            tma_store_2d(&tmap_out, buf, n_tile * BN + cc, m_tile * BM);
+            if (EPI == B200_EPI_GELU_BF16) tma_store_2d(&tmap_out2, buf + EPI_BUF_BYTES / 2, n_tile * BN + cc, m_tile * BM);
+            tma_commit_group();
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (et == 0) tma_wait_group<0>();    // all bulk stores complete before the CTA exits
+    } else
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       int m_tile, n_tile, split;
       decode_work(p, w, m_tile, n_tile, split);
@@ -435,8 +544,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmParams& p,
-                       int grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                       const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -444,21 +553,21 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, to, p);
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, to, to2, p);
   B200_CHECK_LAUNCH("gemm_kernel launch");
   return 0;
 }
 
 template <int BN, bool A_MN, bool B_MN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
-                        const GemmParams& p, int grid, cudaStream_t s) {
+                        const CUtensorMap& to2, const GemmParams& p, int grid, cudaStream_t s) {
   switch (epi) {
-    case B200_EPI_STORE_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_BF16>(ta, tb, to, p, grid, s);
-    case B200_EPI_GELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_GELU_BF16>(ta, tb, to, p, grid, s);
-    case B200_EPI_RESID_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_RESID_F32>(ta, tb, to, p, grid, s);
-    case B200_EPI_DGELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_DGELU_BF16>(ta, tb, to, p, grid, s);
-    case B200_EPI_REDUCE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_REDUCE_F32>(ta, tb, to, p, grid, s);
-    case B200_EPI_STORE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_F32>(ta, tb, to, p, grid, s);
+    case B200_EPI_STORE_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_BF16>(ta, tb, to, to2, p, grid, s);
+    case B200_EPI_GELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_GELU_BF16>(ta, tb, to, to2, p, grid, s);
+    case B200_EPI_RESID_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_RESID_F32>(ta, tb, to, to2, p, grid, s);
+    case B200_EPI_DGELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_DGELU_BF16>(ta, tb, to, to2, p, grid, s);
+    case B200_EPI_REDUCE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_REDUCE_F32>(ta, tb, to, to2, p, grid, s);
+    case B200_EPI_STORE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_F32>(ta, tb, to, to2, p, grid, s);
   }
   set_last_error("b200_gemm_bf16: unknown epilogue %d", epi);
   return -1;
@@ -569,8 +678,9 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   if (epilogue == B200_EPI_RESID_F32 || epilogue == B200_EPI_DGELU_BF16)
     B200_CHECK_ARG(aux != nullptr, "epilogue %d needs aux", epilogue);
 
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, to, to2;
   memset(&to, 0, sizeof(to));
+  memset(&to2, 0, sizeof(to2));
   int rc;
   {
     // A: K-major -> global [M rows][K cols]; MN-major -> global [K rows][M cols]
@@ -593,17 +703,37 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
       rc = make_tmap(&to, out, TMA_F32, 2, dims, strides, box, TMA_SWIZZLE_128B);
       if (rc) return rc;
     }
+    // bf16 outputs leave through TMA stores when base and row pitch are 16-byte aligned (else: per-thread stores)
+    p.tma_epi = 0;
+    if (epilogue == B200_EPI_STORE_BF16 && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      dims[0] = (uint64_t)N; dims[1] = (uint64_t)M; box[0] = 64; box[1] = BM;
+      strides[0] = (uint64_t)ldo * 2;
+      rc = make_tmap(&to, out, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
+      if (rc) return rc;
+      p.tma_epi = 1;
+    }
+    if (epilogue == B200_EPI_GELU_BF16 && ldo % 8 == 0 && ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(out2) & 15) == 0) {
+      dims[0] = (uint64_t)N; dims[1] = (uint64_t)M; box[0] = 32; box[1] = BM;
+      strides[0] = (uint64_t)ldo * 2;
+      rc = make_tmap(&to, out, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_64B);
+      if (rc) return rc;
+      strides[0] = (uint64_t)ldo2 * 2;
+      rc = make_tmap(&to2, out2, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_64B);
+      if (rc) return rc;
+      p.tma_epi = 1;
+    }
   }
   int grid = tiles * p.splits;
   if (grid > sms) grid = sms;
 
   if (BN == 256) {
-    if (combo == 0) return dispatch_epi<256, false, false>(epilogue, ta, tb, to, p, grid, stream);
-    if (combo == 1) return dispatch_epi<256, false, true>(epilogue, ta, tb, to, p, grid, stream);
-    return dispatch_epi<256, true, true>(epilogue, ta, tb, to, p, grid, stream);
+    if (combo == 0) return dispatch_epi<256, false, false>(epilogue, ta, tb, to, to2, p, grid, stream);
+    if (combo == 1) return dispatch_epi<256, false, true>(epilogue, ta, tb, to, to2, p, grid, stream);
+    return dispatch_epi<256, true, true>(epilogue, ta, tb, to, to2, p, grid, stream);
   } else {
-    if (combo == 0) return dispatch_epi<128, false, false>(epilogue, ta, tb, to, p, grid, stream);
-    if (combo == 1) return dispatch_epi<128, false, true>(epilogue, ta, tb, to, p, grid, stream);
-    return dispatch_epi<128, true, true>(epilogue, ta, tb, to, p, grid, stream);
+    if (combo == 0) return dispatch_epi<128, false, false>(epilogue, ta, tb, to, to2, p, grid, stream);
+    if (combo == 1) return dispatch_epi<128, false, true>(epilogue, ta, tb, to, to2, p, grid, stream);
+    return dispatch_epi<128, true, true>(epilogue, ta, tb, to, to2, p, grid, stream);
   }
 }
