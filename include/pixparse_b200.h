@@ -173,6 +173,9 @@ int b200_attention_bwd_dropout(const void* q, long long ldq, int q_col0, const v
 
 /* bring-up aid: override the UMMA shared-memory descriptor fields (-1 keeps the default) */
 int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv);
+/* Bring-up / A-B switch: on = 1 makes b200_gemm_bf16 use one CTA per 128-row tile everywhere instead of CTA pairs
+ * (tcgen05 cta_group::2, 256-row tiles) for the 256-column tile width. Results are identical either way. */
+int b200_debug_gemm_single_cta(int on);
 
 #ifdef __cplusplus
 }

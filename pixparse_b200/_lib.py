@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200_abi_version": [],
     "b200_device_check": [],
     "b200_debug_gemm_desc": [_I, _I, _I, _I, _I, _I],
+    "b200_debug_gemm_single_cta": [_I],
     "b200_attention_fwd": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "b200_attention_fwd_strided": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I,
                                    _F, _P],

@@ -48,13 +48,16 @@ struct GemmParams {
 
 // debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
 static int g_desc_override[6] = {-1, -1, -1, -1, -1, -1};
+static int g_force_single_cta = 0;      // bring-up / A-B switch: 1 = never use CTA pairs, -1 = pairs for every epilogue
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile; each CTA
+// stages its own 128 rows of A and BN / 2 rows of B, so a k-block costs 32 KB of L2 -> SM traffic per SM instead of 48.
+template <int BN, int CG>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (256 or 512 columns: powers of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 256 + 1024 /* bias */ + 1024 /* align */;
 };
@@ -225,12 +228,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -246,6 +249,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pairs: rank inside the pair (0 = leader, issues the MMAs), work items are distributed over pairs
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int worker = (CG == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int n_workers = (CG == 2) ? (int)cluster_count_x() : (int)gridDim.x;
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -260,16 +267,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 256);
+      mbar_init(&tmem_empty_bar[i], 256 * CG);     // the leader collects the epilogue threads of both CTAs
     }
     fence_mbar_init();
   }
   if (warp == 10) {
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();     // barrier inits of both CTAs visible before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -283,14 +296,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = worker; w < total_work; w += n_workers) {
         int m_tile, n_tile, split;
         decode_work(p, w, m_tile, n_tile, split);
+        if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;      // this CTA's 128 rows of the pair's 256
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (elect_one()) {
+          if (CG == 2) {
+            // both CTAs load into their own shared memory; all bytes are credited to the LEADER's full barrier
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              uint8_t* sb = sa + Cfg::A_BYTES;
+              const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              const int nb = n_tile * BN + (int)cta_rank * (BN / 2);   // this CTA's half of the B columns
+              if (!A_MN) {
+                tma_load_2d_pair(sa, &tmap_a, lbar, kb * BK, m_tile * BM);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BM / 64; ++j)
+                  tma_load_2d_pair(sa + j * (BK * 128), &tmap_a, lbar, m_tile * BM + j * 64, kb * BK);
+              }
+              if (!B_MN) {
+                tma_load_2d_pair(sb, &tmap_b, lbar, kb * BK, nb);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 2 / 64; ++j)
+                  tma_load_2d_pair(sb + j * (BK * 128), &tmap_b, lbar, nb + j * 64, kb * BK);
+              }
+            }
+          } else if (elect_one()) {
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -319,13 +356,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp == 9) {
     // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
-    {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (CG == 1 || cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = worker; w < total_work; w += n_workers) {
         int m_tile, n_tile, split;
         decode_work(p, w, m_tile, n_tile, split);
         const int kb0 = split * p.kb_per_split;
@@ -343,11 +380,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_ss(tmem_d, da + (uint64_t)(k * p.a_kadv), db + (uint64_t)(k * p.b_kadv), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+              if (CG == 2)
+                umma_ss_pair(tmem_d, da + (uint64_t)(k * p.a_kadv), db + (uint64_t)(k * p.b_kadv), idesc,
+                             (kb > kb0 || k > 0) ? 1u : 0u);
+              else
+                umma_ss(tmem_d, da + (uint64_t)(k * p.a_kadv), db + (uint64_t)(k * p.b_kadv), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
-            if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
+            if (CG == 2) {
+              umma_commit_pair(&empty_bar[stage]);                          // frees the slot in both CTAs
+              if (kb == kb1 - 1) umma_commit_pair(&tmem_full_bar[acc]);     // wakes the epilogue of both CTAs
+            } else {
+              umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+              if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -387,9 +433,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int swz = (EPI == B200_EPI_STORE_BF16) ? (row_in_tile & 7) : ((row_in_tile >> 1) & 3);
       const uint32_t rowp = buf_s + row_in_tile * (CW * 2);
       const float drop_sc = dropout_scale(p.drop_threshold16);
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = worker; w < total_work; w += n_workers) {
         int m_tile, n_tile, split;
         decode_work(p, w, m_tile, n_tile, split);
+        if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
         if (p.bias != nullptr) {
           if (et < BN / 2) {
             const int col = n_tile * BN + (grp + 2 * (et / CW)) * CW + (et % CW);
@@ -410,7 +457,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tmem_ld_wait();
           if (rd == ROUNDS - 1) {          // last TMEM read of this accumulator stage: hand it back to the MMA warp
             tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[acc]);
+            if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+            else mbar_arrive(&tmem_empty_bar[acc]);
           }
           uint32_t o[CW / 2];
           uint32_t o2[EPI == B200_EPI_GELU_BF16 ? CW / 2 : 1];
@@ -476,9 +524,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (et == 0) tma_wait_group<0>();    // all bulk stores complete before the CTA exits
     } else
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = worker; w < total_work; w += n_workers) {
       int m_tile, n_tile, split;
       decode_work(p, w, m_tile, n_tile, split);
+      if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
@@ -495,7 +544,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (c + 2 >= BN / EPI_COLS) {
           // this thread's last TMEM read of the accumulator stage: hand it back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[acc]);
+          if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+            else mbar_arrive(&tmem_empty_bar[acc]);
         }
         // the staging buffer must be free: previous phase 2 done / previous TMA reduce has read it
         if (EPI == B200_EPI_REDUCE_F32) {
@@ -536,38 +586,70 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 10) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if (CG == 2) {
+    cluster_sync_all();      // the peer's TMEM, barriers and shared memory stay alive until both CTAs are done
+    if (warp == 10) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == 10) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
-                       const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
+static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                          const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG>;
+  constexpr int SMEM = GemmCfg<BN, CG>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tb, to, to2, p);
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, p);
+    if (e != cudaSuccess) return check_cuda(e, "gemm_kernel (CTA pair) launch");
+  } else {
+    kern<<<grid, GEMM_THREADS, SMEM, stream>>>(ta, tb, to, to2, p);
+  }
   B200_CHECK_LAUNCH("gemm_kernel launch");
   return 0;
 }
 
+// p.m_tiles counts 256-row pair tiles when cta_pairs is set (BN = 256 only)
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                       const GemmParams& p, int grid, bool cta_pairs, cudaStream_t stream) {
+  if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2>(ta, tb, to, to2, p, grid, stream);
+  return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1>(ta, tb, to, to2, p, grid, stream);
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
-                        const CUtensorMap& to2, const GemmParams& p, int grid, cudaStream_t s) {
+                        const CUtensorMap& to2, const GemmParams& p, int grid, bool pairs, cudaStream_t s) {
   switch (epi) {
-    case B200_EPI_STORE_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_BF16>(ta, tb, to, to2, p, grid, s);
-    case B200_EPI_GELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_GELU_BF16>(ta, tb, to, to2, p, grid, s);
-    case B200_EPI_RESID_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_RESID_F32>(ta, tb, to, to2, p, grid, s);
-    case B200_EPI_DGELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_DGELU_BF16>(ta, tb, to, to2, p, grid, s);
-    case B200_EPI_REDUCE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_REDUCE_F32>(ta, tb, to, to2, p, grid, s);
-    case B200_EPI_STORE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_F32>(ta, tb, to, to2, p, grid, s);
+    case B200_EPI_STORE_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_BF16>(ta, tb, to, to2, p, grid, pairs, s);
+    case B200_EPI_GELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_GELU_BF16>(ta, tb, to, to2, p, grid, pairs, s);
+    case B200_EPI_RESID_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_RESID_F32>(ta, tb, to, to2, p, grid, pairs, s);
+    case B200_EPI_DGELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_DGELU_BF16>(ta, tb, to, to2, p, grid, pairs, s);
+    case B200_EPI_REDUCE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_REDUCE_F32>(ta, tb, to, to2, p, grid, pairs, s);
+    case B200_EPI_STORE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_F32>(ta, tb, to, to2, p, grid, pairs, s);
   }
   set_last_error("b200_gemm_bf16: unknown epilogue %d", epi);
   return -1;
@@ -580,6 +662,11 @@ using namespace b200;
 extern "C" int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv) {
   g_desc_override[0] = a_lbo; g_desc_override[1] = a_sbo; g_desc_override[2] = a_kadv;
   g_desc_override[3] = b_lbo; g_desc_override[4] = b_sbo; g_desc_override[5] = b_kadv;
+  return 0;
+}
+
+extern "C" int b200_debug_gemm_single_cta(int on) {
+  g_force_single_cta = on;
   return 0;
 }
 
@@ -631,13 +718,19 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   if (BN == 0) BN = (N >= 192) ? 256 : 128;
   B200_CHECK_ARG(BN == 128 || BN == 256, "b200_gemm_bf16: block_n must be 128 or 256");
 
+  // CTA pairs (256-row tiles) whenever the wide tile is used and there are at least two 128-row tiles
+  // (measured at the train-step shapes: STORE -13 %, wgrad -6 %; the GELU / DGELU / RESID epilogues are bound by their
+  //  own epilogue warps, and coupling two of them behind one accumulator hand-back costs 1-4 %, so they stay single)
+  const bool pair_epi = epilogue == B200_EPI_STORE_BF16 || epilogue == B200_EPI_STORE_F32 || epilogue == B200_EPI_REDUCE_F32;
+  const bool cta_pairs = (BN == 256) && (M > BM) && (g_force_single_cta == 0) && (pair_epi || g_force_single_cta == -1);
+  const int tile_m = cta_pairs ? 2 * BM : BM;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.m_tiles = (M + BM - 1) / BM;
+  p.m_tiles = (M + tile_m - 1) / tile_m;
   p.n_tiles = (N + BN - 1) / BN;
   p.k_blocks = (K + BK - 1) / BK;
   const int tiles = p.m_tiles * p.n_tiles;
-  const int sms = num_sms();
+  const int sms = cta_pairs ? num_sms() / 2 : num_sms();      // workers: CTAs or CTA pairs
   if (epilogue == B200_EPI_REDUCE_F32) {
     if (splits <= 0) {
       // fill the machine: aim for >= 2 work items per SM, but keep >= 8 k-blocks per split
@@ -691,7 +784,7 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     strides[0] = (uint64_t)lda * 2;
     rc = make_tmap(&ta, A, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
     if (rc) return rc;
-    if (!b_mn_major) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)BN; }
+    if (!b_mn_major) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BK; box[1] = (uint32_t)(cta_pairs ? BN / 2 : BN); }
     else             { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)ldb * 2;
     rc = make_tmap(&tb, B, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
@@ -726,14 +819,15 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   }
   int grid = tiles * p.splits;
   if (grid > sms) grid = sms;
+  if (cta_pairs) grid *= 2;
 
   if (BN == 256) {
-    if (combo == 0) return dispatch_epi<256, false, false>(epilogue, ta, tb, to, to2, p, grid, stream);
-    if (combo == 1) return dispatch_epi<256, false, true>(epilogue, ta, tb, to, to2, p, grid, stream);
-    return dispatch_epi<256, true, true>(epilogue, ta, tb, to, to2, p, grid, stream);
+    if (combo == 0) return dispatch_epi<256, false, false>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
+    if (combo == 1) return dispatch_epi<256, false, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
+    return dispatch_epi<256, true, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
   } else {
-    if (combo == 0) return dispatch_epi<128, false, false>(epilogue, ta, tb, to, to2, p, grid, stream);
-    if (combo == 1) return dispatch_epi<128, false, true>(epilogue, ta, tb, to, to2, p, grid, stream);
-    return dispatch_epi<128, true, true>(epilogue, ta, tb, to, to2, p, grid, stream);
+    if (combo == 0) return dispatch_epi<128, false, false>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
+    if (combo == 1) return dispatch_epi<128, false, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
+    return dispatch_epi<128, true, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
   }
 }
