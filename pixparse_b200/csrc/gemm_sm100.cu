@@ -52,14 +52,20 @@ static int g_force_single_cta = 0;      // bring-up / A-B switch: 1 = never use 
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile; each CTA
 // stages its own 128 rows of A and BN / 2 rows of B, so a k-block costs 32 KB of L2 -> SM traffic per SM instead of 48.
-template <int BN, int CG>
+// Epilogues with an aux operand (DGELU: saved pre-activation, RESID: residual stream) stage it in a second 16 KB tile per
+// epilogue group, which costs the ring one stage.
+template <int BN, int CG, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : 6;
+  static constexpr bool HAS_AUX = (EPI == B200_EPI_DGELU_BF16 || EPI == B200_EPI_RESID_F32);
+  static constexpr int EPI_GROUP_BYTES = (HAS_AUX ? 2 : 1) * EPI_BUF_BYTES;
+  static constexpr int TAIL_BYTES = 256 /* barriers */ + 1024 /* bias */ + 1024 /* alignment slack */;
+  static constexpr int MAX_STAGES = (232448 - TAIL_BYTES - 2 * EPI_GROUP_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES < 6 ? MAX_STAGES : 6;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (256 or 512 columns: powers of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 256 + 1024 /* bias */ + 1024 /* align */;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_GROUP_BYTES + TAIL_BYTES;
 };
 
 __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& n_tile, int& split) {
@@ -233,19 +239,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, EPI>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_buf = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + 2 * EPI_BUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + 2 * Cfg::EPI_GROUP_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* epi_bias = reinterpret_cast<float*>(epi_buf + 2 * EPI_BUF_BYTES + 256);   // 2 groups x 128 floats
+  uint64_t* aux_full_bar = tmem_empty_bar + 2;  // [2] per epilogue group: aux tile landed (TMA transaction bytes)
+  uint64_t* aux_free_bar = aux_full_bar + 2;    // [2] per epilogue group: all 128 threads have read the aux tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_free_bar + 2);
+  float* epi_bias = reinterpret_cast<float*>(epi_buf + 2 * Cfg::EPI_GROUP_BYTES + 256);   // 2 groups x 128 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -258,7 +266,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     if (EPI == B200_EPI_REDUCE_F32 || EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_GELU_BF16) prefetch_tmap(&tmap_out);
-    if (EPI == B200_EPI_GELU_BF16) prefetch_tmap(&tmap_out2);
+    if (EPI == B200_EPI_GELU_BF16 || Cfg::HAS_AUX) prefetch_tmap(&tmap_out2);
   }
   if (warp == 11 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -268,6 +276,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 256 * CG);     // the leader collects the epilogue threads of both CTAs
+      mbar_init(&aux_full_bar[i], 1);
+      mbar_init(&aux_free_bar[i], 128);
     }
     fence_mbar_init();
   }
@@ -414,25 +424,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int ew = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
     const int row_in_tile = ew * 32 + lane;    // accumulator row owned in phase 1
     const uint32_t bar_id = 1 + grp;
-    uint8_t* buf = epi_buf + grp * EPI_BUF_BYTES;
+    uint8_t* buf = epi_buf + grp * Cfg::EPI_GROUP_BYTES;
     const uint32_t buf_s = smem_u32(buf);
     int acc = 0;
     uint32_t acc_phase = 0;
-    if ((EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_GELU_BF16) && p.tma_epi) {
-      // ---- bf16 outputs through TMA stores: the math runs in the accumulator's own row-per-thread layout, the packed
-      // result is staged once in the swizzled layout the tensor map expects and leaves as one bulk store per round.
-      // No second pass over shared memory, no per-thread global stores (ncu on the two-pass version: the epilogue
-      // warps, not the tensor pipe, bounded every K = 768 GEMM; 2/3 of their stall samples were scoreboard waits on
-      // the staging reads and on registers held by in-flight STGs).
-      //   STORE: rounds of 64 columns (128-byte rows, SWIZZLE_128B), GELU: rounds of 32 columns, two 64-byte-row tiles
-      //   (pre-activation and activation, SWIZZLE_64B).
-      constexpr int CW = (EPI == B200_EPI_STORE_BF16) ? 64 : 32;
+    if ((EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_GELU_BF16 || Cfg::HAS_AUX) && p.tma_epi) {
+      // ---- outputs (and the aux operand) move by TMA: the math runs in the accumulator's own row-per-thread layout,
+      // the result is staged once in the swizzled layout the tensor map expects and leaves as one bulk store per
+      // round; the aux tile of the NEXT round is in flight while this one is computed. No second pass over shared
+      // memory, no per-thread global loads / stores (ncu on the two-pass version: the epilogue warps, not the tensor
+      // pipe, bounded every K = 768 GEMM; 2/3 of their stall samples were scoreboard waits on the staging reads, on
+      // the aux registers and on registers held by in-flight STGs).
+      //   STORE: rounds of 64 columns (bf16, 128-byte rows)      GELU: rounds of 32 columns, two 64-byte-row tiles
+      //   DGELU: rounds of 64 columns, aux tile bf16             RESID: rounds of 32 columns, fp32 out and aux tiles
+      constexpr bool AUX = Cfg::HAS_AUX;
+      constexpr int CW = (EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_DGELU_BF16) ? 64 : 32;
       constexpr int ROUNDS = BN / CW / 2;            // per group and tile; the groups take alternating rounds
+      constexpr bool OUT_F32 = (EPI == B200_EPI_RESID_F32);
       float* sbias = epi_bias + grp * 128;           // bias of this group's BN / 2 columns, [round][CW]
       const uint32_t sbias_s = smem_u32(sbias);
-      const int swz = (EPI == B200_EPI_STORE_BF16) ? (row_in_tile & 7) : ((row_in_tile >> 1) & 3);
-      const uint32_t rowp = buf_s + row_in_tile * (CW * 2);
+      const int swz = (EPI == B200_EPI_GELU_BF16) ? ((row_in_tile >> 1) & 3) : (row_in_tile & 7);
+      const uint32_t rowp = buf_s + row_in_tile * (EPI == B200_EPI_GELU_BF16 ? 64 : 128);
+      uint8_t* aux_tile = buf + EPI_BUF_BYTES;       // (AUX only)
+      const uint32_t auxp = buf_s + EPI_BUF_BYTES + row_in_tile * 128;
       const float drop_sc = dropout_scale(p.drop_threshold16);
+      uint32_t aux_phase = 0;
+      auto issue_aux = [&](int m_t, int n_t, int rd) {       // thread 0 of the group
+        mbar_expect_tx(&aux_full_bar[grp], EPI_BUF_BYTES);
+        tma_load_2d(aux_tile, &tmap_out2, &aux_full_bar[grp], n_t * BN + (grp + 2 * rd) * CW, m_t * BM);
+      };
+      if (AUX && et == 0 && worker < total_work) {
+        int m_t, n_t, sp;
+        decode_work(p, worker, m_t, n_t, sp);
+        if (CG == 2) m_t = m_t * 2 + (int)cta_rank;
+        issue_aux(m_t, n_t, 0);
+      }
       for (int w = worker; w < total_work; w += n_workers) {
         int m_tile, n_tile, split;
         decode_work(p, w, m_tile, n_tile, split);
@@ -454,13 +480,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           uint32_t r[CW];
           tmem_ld_32x32_at<0>(taddr + cc, r);
           if (CW == 64) tmem_ld_32x32_at<(CW == 64 ? 32 : 0)>(taddr + cc + 32, r);
+          uint32_t ax[AUX ? 32 : 1];                 // aux row: 64 bf16 (DGELU) or 32 fp32 (RESID)
+          if (AUX) {
+            mbar_wait(&aux_full_bar[grp], aux_phase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 t4 = lds128(auxp + ((j ^ swz) << 4));
+              ax[AUX ? 4 * j : 0] = t4.x; ax[AUX ? 4 * j + 1 : 0] = t4.y; ax[AUX ? 4 * j + 2 : 0] = t4.z; ax[AUX ? 4 * j + 3 : 0] = t4.w;
+            }
+            mbar_arrive(&aux_free_bar[grp]);
+            if (et == 0) {
+              // refill the aux tile for the next round of this group (possibly the next tile) as soon as all have read it
+              mbar_wait(&aux_free_bar[grp], aux_phase);
+              if (rd + 1 < ROUNDS) {
+                issue_aux(m_tile, n_tile, rd + 1);
+              } else if (w + n_workers < total_work) {
+                int m_t, n_t, sp;
+                decode_work(p, w + n_workers, m_t, n_t, sp);
+                if (CG == 2) m_t = m_t * 2 + (int)cta_rank;
+                issue_aux(m_t, n_t, 0);
+              }
+            }
+            aux_phase ^= 1;
+          }
           tmem_ld_wait();
           if (rd == ROUNDS - 1) {          // last TMEM read of this accumulator stage: hand it back to the MMA warp
             tc_fence_before();
             if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
             else mbar_arrive(&tmem_empty_bar[acc]);
           }
-          uint32_t o[CW / 2];
+          uint32_t o[OUT_F32 ? CW : CW / 2];
           uint32_t o2[EPI == B200_EPI_GELU_BF16 ? CW / 2 : 1];
 #pragma unroll
           for (int q = 0; q < CW / 4; ++q) {
@@ -471,38 +520,66 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               v01 = f2_add(v01, f2_pack(__uint_as_float(bq.x), __uint_as_float(bq.y)));
               v23 = f2_add(v23, f2_pack(__uint_as_float(bq.z), __uint_as_float(bq.w)));
             }
+            f32x2 dm01 = 0ull, dm23 = 0ull;
+            const bool drop_on = (EPI != B200_EPI_STORE_BF16) && p.drop_threshold16 != 0u;
+            if (drop_on) {
+              const uint32_t pair = (uint32_t)(((long long)grow * p.N + (n_tile * BN + cc + 4 * q)) >> 1);
+              float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
+              dropout_pair(p.drop_seed, pair, p.drop_threshold16, drop_sc, d0, d1);
+              dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, drop_sc, d2, d3);
+              dm01 = f2_pack(d0, d1);
+              dm23 = f2_pack(d2, d3);
+              if (AUX) {                    // RESID drops (acc + bias), DGELU masks the incoming gradient
+                v01 = f2_mul(v01, dm01);
+                v23 = f2_mul(v23, dm23);
+              }
+            }
             float v0, v1, v2, v3;
-            f2_unpack(v01, v0, v1);
-            f2_unpack(v23, v2, v3);
-            const uint32_t h01 = pack_bf16(v0, v1), h23 = pack_bf16(v2, v3);
             if (EPI == B200_EPI_STORE_BF16) {
-              o[2 * q] = h01;
-              o[2 * q + 1] = h23;
-            } else {
+              f2_unpack(v01, v0, v1);
+              f2_unpack(v23, v2, v3);
+              o[2 * q] = pack_bf16(v0, v1);
+              o[2 * q + 1] = pack_bf16(v2, v3);
+            } else if (EPI == B200_EPI_GELU_BF16) {
               // out2 = pre-activation h (bf16); out = gelu(h) evaluated on the ROUNDED h (what autocast feeds nn.GELU)
+              f2_unpack(v01, v0, v1);
+              f2_unpack(v23, v2, v3);
+              const uint32_t h01 = pack_bf16(v0, v1), h23 = pack_bf16(v2, v3);
               o2[EPI == B200_EPI_GELU_BF16 ? 2 * q : 0] = h01;
               o2[EPI == B200_EPI_GELU_BF16 ? 2 * q + 1 : 0] = h23;
               f32x2 g01 = gelu_erf2(f2_pack(bf16_lo(h01), bf16_hi(h01)));
               f32x2 g23 = gelu_erf2(f2_pack(bf16_lo(h23), bf16_hi(h23)));
-              if (p.drop_threshold16 != 0u) {
-                const uint32_t pair = (uint32_t)(((long long)grow * p.N + (n_tile * BN + cc + 4 * q)) >> 1);
-                float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
-                dropout_pair(p.drop_seed, pair, p.drop_threshold16, drop_sc, d0, d1);
-                dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, drop_sc, d2, d3);
-                g01 = f2_mul(g01, f2_pack(d0, d1));
-                g23 = f2_mul(g23, f2_pack(d2, d3));
+              if (drop_on) {
+                g01 = f2_mul(g01, dm01);
+                g23 = f2_mul(g23, dm23);
               }
               f2_unpack(g01, v0, v1);
               f2_unpack(g23, v2, v3);
               o[2 * q] = pack_bf16(v0, v1);
               o[2 * q + 1] = pack_bf16(v2, v3);
+            } else if (EPI == B200_EPI_DGELU_BF16) {
+              // out = acc * gelu'(h), h = saved bf16 pre-activation (aux)
+              const uint32_t h01 = ax[AUX ? 2 * q : 0], h23 = ax[AUX ? 2 * q + 1 : 0];
+              f2_unpack(f2_mul(v01, gelu_erf_grad2(f2_pack(bf16_lo(h01), bf16_hi(h01)))), v0, v1);
+              f2_unpack(f2_mul(v23, gelu_erf_grad2(f2_pack(bf16_lo(h23), bf16_hi(h23)))), v2, v3);
+              o[2 * q] = pack_bf16(v0, v1);
+              o[2 * q + 1] = pack_bf16(v2, v3);
+            } else {
+              // RESID: out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
+              f2_unpack(f2_add(v01, f2_pack(__uint_as_float(ax[AUX ? 4 * q : 0]), __uint_as_float(ax[AUX ? 4 * q + 1 : 0]))), v0, v1);
+              f2_unpack(f2_add(v23, f2_pack(__uint_as_float(ax[AUX ? 4 * q + 2 : 0]), __uint_as_float(ax[AUX ? 4 * q + 3 : 0]))), v2, v3);
+              o[OUT_F32 ? 4 * q : 0] = __float_as_uint(v0);
+              o[OUT_F32 ? 4 * q + 1 : 0] = __float_as_uint(v1);
+              o[OUT_F32 ? 4 * q + 2 : 0] = __float_as_uint(v2);
+              o[OUT_F32 ? 4 * q + 3 : 0] = __float_as_uint(v3);
             }
           }
           // the staging tile(s) must be free: the previous round's bulk store has finished reading them
           if (et == 0) tma_wait_group_read<0>();
           named_bar_sync(bar_id, 128);
+          constexpr int PIECES = (EPI == B200_EPI_GELU_BF16) ? 4 : 8;     // 16-byte pieces per staged row
 #pragma unroll
-          for (int j = 0; j < CW / 8; ++j) {
+          for (int j = 0; j < PIECES; ++j) {
             sts128(rowp + ((j ^ swz) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             if (EPI == B200_EPI_GELU_BF16)
               sts128(rowp + EPI_BUF_BYTES / 2 + ((j ^ swz) << 4), o2[EPI == B200_EPI_GELU_BF16 ? 4 * j : 0],
@@ -602,7 +679,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
 static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                           const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG>;
-  constexpr int SMEM = GemmCfg<BN, CG>::SMEM_BYTES;
+  constexpr int SMEM = GemmCfg<BN, CG, EPI>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -722,7 +799,7 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   // (measured at the train-step shapes: STORE -13 %, wgrad -6 %; the GELU / DGELU / RESID epilogues are bound by their
   //  own epilogue warps, and coupling two of them behind one accumulator hand-back costs 1-4 %, so they stay single)
   const bool pair_epi = epilogue == B200_EPI_STORE_BF16 || epilogue == B200_EPI_STORE_F32 || epilogue == B200_EPI_REDUCE_F32;
-  const bool cta_pairs = (BN == 256) && (M > BM) && (g_force_single_cta == 0) && (pair_epi || g_force_single_cta == -1);
+  const bool cta_pairs = (BN == 256) && (M > BM) && (g_force_single_cta != 1) && (pair_epi || g_force_single_cta == -1);
   const int tile_m = cta_pairs ? 2 * BM : BM;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -813,6 +890,27 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
       if (rc) return rc;
       strides[0] = (uint64_t)ldo2 * 2;
       rc = make_tmap(&to2, out2, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_64B);
+      if (rc) return rc;
+      p.tma_epi = 1;
+    }
+    if (epilogue == B200_EPI_DGELU_BF16 && ldo % 8 == 0 && ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(aux) & 15) == 0) {
+      dims[0] = (uint64_t)N; dims[1] = (uint64_t)M; box[0] = 64; box[1] = BM;
+      strides[0] = (uint64_t)ldo * 2;
+      rc = make_tmap(&to, out, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
+      if (rc) return rc;
+      strides[0] = (uint64_t)ld_aux * 2;
+      rc = make_tmap(&to2, aux, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
+      if (rc) return rc;
+      p.tma_epi = 1;
+    }
+    if (epilogue == B200_EPI_RESID_F32 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0) {   // ldo, ld_aux % 4 checked above
+      dims[0] = (uint64_t)N; dims[1] = (uint64_t)M; box[0] = 32; box[1] = BM;
+      strides[0] = (uint64_t)ldo * 4;
+      rc = make_tmap(&to, out, TMA_F32, 2, dims, strides, box, TMA_SWIZZLE_128B);
+      if (rc) return rc;
+      strides[0] = (uint64_t)ld_aux * 4;
+      rc = make_tmap(&to2, aux, TMA_F32, 2, dims, strides, box, TMA_SWIZZLE_128B);
       if (rc) return rc;
       p.tma_epi = 1;
     }

@@ -3,8 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pixparse_b200 import ops, _lib
-if os.environ.get("SINGLE_CTA"):
-    _lib.lib().b200_debug_gemm_single_cta(1)
+if os.environ.get("SINGLE_CTA"):      # 1 = never CTA pairs, -1 = CTA pairs for every epilogue
+    _lib.lib().b200_debug_gemm_single_cta(int(os.environ["SINGLE_CTA"]))
 which = sys.argv[1] if len(sys.argv) > 1 else "gelu"
 M, D, F = 32 * 1009, 768, 3072
 torch.manual_seed(0)
