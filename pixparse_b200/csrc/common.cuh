@@ -404,31 +404,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2) ------------------------------------------------
 // A 3-register FFMA issues every second cycle per SM sub-partition; the f32x2 forms do two lanes' worth per issue, so
 // the fp32-heavy epilogues (bias, GELU, GELU', dropout scaling) cost half the fma-pipe slots.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ f32x2 f2_splat(float v) { return f2_pack(v, v); }
+// (the float2 intrinsics of sm_100_rt.h rather than inline PTX on .b64 registers: with the asm form ptxas spent a
+//  quarter of the GELU epilogue's instructions on IMAD.MOV register-pair shuffles, with the intrinsics none)
+typedef float2 f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { return make_float2(lo, hi); }
+__device__ __forceinline__ f32x2 f2_splat(float v) { return make_float2(v, v); }
 __device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  lo = v.x;
+  hi = v.y;
 }
-__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { return __fadd2_rn(a, b); }
 // pair forms of gelu_erf / gelu_erf_grad (same polynomial; the clamp moves to x^2 <= 36, one FMNMX per lane:
 // beyond |x| = 6 the tanh argument keeps growing linearly with the positive slope p(36), so tanh -> +-1 as it must)
 __device__ __forceinline__ f32x2 gelu_tanh2(f32x2 x, f32x2& x2c) {

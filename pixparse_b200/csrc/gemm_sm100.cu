@@ -143,7 +143,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_
       // fp32 pairs: the arithmetic below runs on the packed FFMA2 / FMUL2 / FADD2 forms (half the fma-pipe issue slots)
       f32x2 v01 = f2_add(f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y)), b01);
       f32x2 v23 = f2_add(f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w)), b23);
-      f32x2 dm01 = 0ull, dm23 = 0ull;         // dropout multipliers of the 4 columns (N is even when dropout is on)
+      f32x2 dm01 = f2_splat(0.f), dm23 = f2_splat(0.f);         // dropout multipliers of the 4 columns (N is even when dropout is on)
       const bool drop_on = (EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16) &&
                            p.drop_threshold16 != 0u;
       if (drop_on) {
@@ -520,7 +520,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               v01 = f2_add(v01, f2_pack(__uint_as_float(bq.x), __uint_as_float(bq.y)));
               v23 = f2_add(v23, f2_pack(__uint_as_float(bq.z), __uint_as_float(bq.w)));
             }
-            f32x2 dm01 = 0ull, dm23 = 0ull;
+            f32x2 dm01 = f2_splat(0.f), dm23 = f2_splat(0.f);
             const bool drop_on = (EPI != B200_EPI_STORE_BF16) && p.drop_threshold16 != 0u;
             if (drop_on) {
               const uint32_t pair = (uint32_t)(((long long)grow * p.N + (n_tile * BN + cc + 4 * q)) >> 1);

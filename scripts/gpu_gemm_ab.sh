@@ -3,7 +3,7 @@
 # usage: bash scripts/gpu_gemm_ab.sh [lib.so ...]   (paths relative to pixparse_b200/csrc; default: the in-tree build)
 mkdir -p gpurun_out
 libs="${@:-libpixparse_b200.so}"
-for rep in 1 2; do
+for rep in 1; do
   for l in $libs; do
     for mode in auto allpair single; do
       echo "== $l $mode"
