@@ -237,6 +237,14 @@ def run_b200_arm(args):
     prof = _lib.profile_ops(lambda: device_step(0), names=("b200_gemm_bf16", "b200_attention_fwd",
                                                            "b200_attention_bwd"), repeats=2)
     barrier()
+    if args.profile_all and rank == 0:
+        allp = _lib.profile_ops(lambda: device_step(0), names=tuple(_lib.SIGNATURES.keys()), repeats=2)
+        rows = sorted(((v["ms"], n, v["calls"]) for n, v in allp.items() if v["calls"]), reverse=True)
+        with open(args.profile_all, "w") as fh:
+            fh.write(f"per-step device time by entry point (CUDA events around each call; step = {ms_step:.2f} ms)\n")
+            for ms, n, calls in rows:
+                fh.write(f"{ms:9.3f} ms  {100 * ms / ms_step:5.1f}%  calls={calls:4d}  avg={1e3 * ms / calls:8.1f} us  {n}\n")
+            fh.write(f"{sum(r[0] for r in rows):9.3f} ms  total of the above\n")
     gemm_ms, gemm_flops, gemm_n = prof["b200_gemm_bf16"]["ms"], prof["b200_gemm_bf16"]["flops"], prof["b200_gemm_bf16"]["calls"]
     att_ms = prof["b200_attention_fwd"]["ms"] + prof["b200_attention_bwd"]["ms"]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -299,6 +307,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="pages per GPU (BASELINE config: 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout-off", action="store_true", help="diagnostic only: the reference trains with dropout 0.1")
+    ap.add_argument("--profile-all", default=None, metavar="FILE",
+                    help="diagnostic: also time every C-ABI entry point of one step (CUDA events) and write the table to FILE")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

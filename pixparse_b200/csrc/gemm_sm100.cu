@@ -810,10 +810,22 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   const int sms = cta_pairs ? num_sms() / 2 : num_sms();      // workers: CTAs or CTA pairs
   if (epilogue == B200_EPI_REDUCE_F32) {
     if (splits <= 0) {
-      // fill the machine: aim for >= 2 work items per SM, but keep >= 8 k-blocks per split
-      splits = (2 * sms + tiles - 1) / tiles;
+      // Split K so that the work items fill whole waves of the persistent grid: cost model = waves x (k-blocks per item +
+      // ~6 k-blocks of pipeline fill and reduce-add epilogue), >= 8 k-blocks per split. (The former "two items per SM"
+      // rule left the last wave 10-30 % full on every weight-gradient shape of the step.)
       const int max_splits = (p.k_blocks + 7) / 8;
-      if (splits > max_splits) splits = max_splits;
+      long long best_cost = -1;
+      for (int s_try = 1; s_try <= max_splits; ++s_try) {
+        const int kbs = (p.k_blocks + s_try - 1) / s_try;
+        const int s_eff = (p.k_blocks + kbs - 1) / kbs;
+        const long long items = (long long)tiles * s_eff;
+        const long long waves = (items + sms - 1) / sms;
+        const long long cost = waves * (kbs + 6);
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost;
+          splits = s_eff;
+        }
+      }
       if (splits < 1) splits = 1;
     }
   } else {

@@ -25,8 +25,9 @@ elif which == "store":
     bias = torch.randn(3 * D, device="cuda"); o = torch.empty((M, 3 * D), device="cuda", dtype=torch.bfloat16)
     fn = lambda: ops.gemm(A, B, epi=ops.EPI_STORE_BF16, bias=bias, out=o)
 else:
-    A = torch.randn((M, F), device="cuda").bfloat16(); B = torch.randn((M, D), device="cuda").bfloat16()
-    o = torch.zeros((F, D), device="cuda")
+    NO = {"wgrad": F, "wgrad_qkv": 3 * D, "wgrad_proj": D}[which]       # dW [NO, D] = dy[M, NO]^T x[M, D]
+    A = torch.randn((M, NO), device="cuda").bfloat16(); B = torch.randn((M, D), device="cuda").bfloat16()
+    o = torch.zeros((NO, D), device="cuda")
     fn = lambda: ops.gemm(A, B, a_mn=True, b_mn=True, epi=ops.EPI_REDUCE_F32, out=o)
 for _ in range(3): fn()
 torch.cuda.synchronize()
