@@ -23,8 +23,21 @@ colsum_bf16_kernel(const bf16* __restrict__ dy, long long ld, int rows, int cols
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (col < cols) {   // cols is a multiple of 8
-    for (int r = r0 + rl; r < r1; r += 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(dy + (long long)r * ld + col);
+    const bf16* src = dy + col;
+    int r = r0 + rl;
+    // four independent 16-byte loads in flight per thread (the rolled loop ran at ~4.5 of ~7 TB/s)
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (long long)(r + 8 * u) * ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
+        acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)r * ld));
       acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
       acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
     }
@@ -185,7 +198,7 @@ extern "C" int b200_colsum_bf16(const void* dy, long long ld, int rows, int cols
   B200_CHECK_ARG(dy && out && rows > 0 && cols > 0, "b200_colsum_bf16: bad arguments");
   B200_CHECK_ARG(cols % 8 == 0 && ld % 8 == 0, "b200_colsum_bf16: cols and ld must be multiples of 8");
   const int col_blocks = (cols + 255) / 256;
-  int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+  int row_blocks = (num_sms() * 8 + col_blocks - 1) / col_blocks;
   int rows_per_block = (rows + row_blocks - 1) / row_blocks;
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   row_blocks = (rows + rows_per_block - 1) / rows_per_block;

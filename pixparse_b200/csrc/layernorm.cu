@@ -175,7 +175,18 @@ static int ln_bwd_launch(const bf16* dy16, const float* dy32, const float* dres3
                          const float* rstd, const float* gamma, float* dx32, bf16* dx16, float* dgamma, float* dbeta,
                          int rows, uint32_t in_thr, uint32_t in_seed, uint32_t out_thr, uint32_t out_seed,
                          cudaStream_t s) {
-  int grid = num_sms() * 4;
+  // exactly one wave of resident CTAs: every CTA strides over the rows, so a partial second wave (the former fixed
+  // 4 CTAs per SM against 3 that fit) ran at a quarter of the memory parallelism for a third of the rows
+  static int per_sm[2] = {0, 0};
+  const bool drop = in_thr != 0u || out_thr != 0u;
+  if (per_sm[drop] == 0) {
+    int n = 0;
+    cudaError_t e = drop ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_kernel<NV, true>, LN_WARPS * 32, 0)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_kernel<NV, false>, LN_WARPS * 32, 0);
+    if (e != cudaSuccess) return check_cuda(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(layernorm_bwd)");
+    per_sm[drop] = n > 0 ? n : 1;
+  }
+  int grid = num_sms() * per_sm[drop];
   const int need = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > need) grid = need;
   if (in_thr != 0u || out_thr != 0u)
