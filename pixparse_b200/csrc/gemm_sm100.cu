@@ -48,7 +48,7 @@ struct GemmParams {
 
 // debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
 static int g_desc_override[6] = {-1, -1, -1, -1, -1, -1};
-static int g_force_single_cta = 0;      // bring-up / A-B switch: 1 = never use CTA pairs, -1 = pairs for every epilogue
+static int g_force_single_cta = 0;      // bring-up / A-B switch: 1 = never use CTA pairs
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile; each CTA
 // stages its own 128 rows of A and BN / 2 rows of B, so a k-block costs 32 KB of L2 -> SM traffic per SM instead of 48.
@@ -60,7 +60,10 @@ struct GemmCfg {
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr bool HAS_AUX = (EPI == B200_EPI_DGELU_BF16 || EPI == B200_EPI_RESID_F32);
-  static constexpr int EPI_GROUP_BYTES = (HAS_AUX ? 2 : 1) * EPI_BUF_BYTES;
+  // aux tiles per epilogue group: two (prefetch distance of two rounds: one round is shorter than an HBM round trip
+  // under load) wherever the ring can spare the space
+  static constexpr int NAUX = HAS_AUX ? ((CG == 2 || BN == 128) ? 2 : 1) : 0;
+  static constexpr int EPI_GROUP_BYTES = (1 + (EPI == B200_EPI_GELU_BF16 ? 1 : NAUX)) * EPI_BUF_BYTES;
   static constexpr int TAIL_BYTES = 256 /* barriers */ + 1024 /* bias */ + 1024 /* alignment slack */;
   static constexpr int MAX_STAGES = (232448 - TAIL_BYTES - 2 * EPI_GROUP_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES < 6 ? MAX_STAGES : 6;
@@ -113,7 +116,7 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, int row0,
   }
 }
 
-template <int EPI, bool INTERIOR>
+template <int EPI, bool INTERIOR, bool DROP>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_s, int et, int row0, int col,
                                               const EpiAux& aux) {
   const int cq = et & 7;
@@ -144,8 +147,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_
       f32x2 v01 = f2_add(f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y)), b01);
       f32x2 v23 = f2_add(f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w)), b23);
       f32x2 dm01 = f2_splat(0.f), dm23 = f2_splat(0.f);         // dropout multipliers of the 4 columns (N is even when dropout is on)
-      const bool drop_on = (EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16) &&
-                           p.drop_threshold16 != 0u;
+      constexpr bool drop_on = DROP;      // (a kernel variant of its own: the mask code doubles the epilogue's size)
       if (drop_on) {
         const uint32_t pair = (uint32_t)(((long long)(row0 + 16 * i) * p.N + col) >> 1);
         const float sc = dropout_scale(p.drop_threshold16);
@@ -234,7 +236,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
@@ -250,9 +252,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
-  uint64_t* aux_full_bar = tmem_empty_bar + 2;  // [2] per epilogue group: aux tile landed (TMA transaction bytes)
-  uint64_t* aux_free_bar = aux_full_bar + 2;    // [2] per epilogue group: all 128 threads have read the aux tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_free_bar + 2);
+  uint64_t* aux_full_bar = tmem_empty_bar + 2;  // [group][slot]: aux tile landed (TMA transaction bytes)
+  uint64_t* aux_free_bar = aux_full_bar + 4;    // [group][slot]: all 128 threads of the group have read the aux tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_free_bar + 4);
   float* epi_bias = reinterpret_cast<float*>(epi_buf + 2 * Cfg::EPI_GROUP_BYTES + 256);   // 2 groups x 128 floats
 
   const int warp = threadIdx.x >> 5;
@@ -276,8 +278,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 256 * CG);     // the leader collects the epilogue threads of both CTAs
-      mbar_init(&aux_full_bar[i], 1);
-      mbar_init(&aux_free_bar[i], 128);
+      for (int j = 0; j < 2; ++j) {
+        mbar_init(&aux_full_bar[2 * i + j], 1);
+        mbar_init(&aux_free_bar[2 * i + j], 128);
+      }
     }
     fence_mbar_init();
   }
@@ -435,29 +439,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // memory, no per-thread global loads / stores (ncu on the two-pass version: the epilogue warps, not the tensor
       // pipe, bounded every K = 768 GEMM; 2/3 of their stall samples were scoreboard waits on the staging reads, on
       // the aux registers and on registers held by in-flight STGs).
-      //   STORE: rounds of 64 columns (bf16, 128-byte rows)      GELU: rounds of 32 columns, two 64-byte-row tiles
-      //   DGELU: rounds of 64 columns, aux tile bf16             RESID: rounds of 32 columns, fp32 out and aux tiles
+      //   STORE / GELU / DGELU: rounds of 64 columns (bf16, 128-byte rows; GELU stages two tiles, DGELU reads an aux tile)
+      //   RESID: rounds of 32 columns, fp32 out and aux tiles. The accumulator is always read 32 columns at a time.
       constexpr bool AUX = Cfg::HAS_AUX;
-      constexpr int CW = (EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_DGELU_BF16) ? 64 : 32;
-      constexpr int ROUNDS = BN / CW / 2;            // per group and tile; the groups take alternating rounds
       constexpr bool OUT_F32 = (EPI == B200_EPI_RESID_F32);
+      constexpr bool TWO_OUT = (EPI == B200_EPI_GELU_BF16);
+      constexpr int CW = OUT_F32 ? 32 : 64;          // columns per staging round = one 128-byte row of the out tile
+      constexpr int HALVES = CW / 32;                // the accumulator is read 32 columns at a time (register budget)
+      constexpr int ROUNDS = BN / CW / 2;            // per group and tile; the groups take alternating rounds
       float* sbias = epi_bias + grp * 128;           // bias of this group's BN / 2 columns, [round][CW]
       const uint32_t sbias_s = smem_u32(sbias);
-      const int swz = (EPI == B200_EPI_GELU_BF16) ? ((row_in_tile >> 1) & 3) : (row_in_tile & 7);
-      const uint32_t rowp = buf_s + row_in_tile * (EPI == B200_EPI_GELU_BF16 ? 64 : 128);
-      uint8_t* aux_tile = buf + EPI_BUF_BYTES;       // (AUX only)
-      const uint32_t auxp = buf_s + EPI_BUF_BYTES + row_in_tile * 128;
+      const int swz = row_in_tile & 7;
+      const uint32_t rowp = buf_s + row_in_tile * 128;                    // this thread's row of the out tile
+      uint8_t* tile2 = buf + EPI_BUF_BYTES;                               // second tile(s): GELU pre-activation / aux operand
+      const uint32_t row2p = buf_s + EPI_BUF_BYTES + row_in_tile * 128;
       const float drop_sc = dropout_scale(p.drop_threshold16);
-      uint32_t aux_phase = 0;
-      auto issue_aux = [&](int m_t, int n_t, int rd) {       // thread 0 of the group
-        mbar_expect_tx(&aux_full_bar[grp], EPI_BUF_BYTES);
-        tma_load_2d(aux_tile, &tmap_out2, &aux_full_bar[grp], n_t * BN + (grp + 2 * rd) * CW, m_t * BM);
-      };
-      if (AUX && et == 0 && worker < total_work) {
+      constexpr int NAUX = AUX ? Cfg::NAUX : 1;              // aux tiles in flight = prefetch distance in rounds
+      uint32_t aux_seq = 0;                                  // rounds consumed by this group: slot = seq % NAUX
+      // thread 0 of the group: start the aux load of the round `ahead` rounds after (work item w, round rd)
+      auto issue_aux = [&](int w, int rd, int ahead, uint32_t seq) {
+        rd += ahead;
+        while (rd >= ROUNDS) {
+          rd -= ROUNDS;
+          w += n_workers;
+        }
+        if (w >= total_work) return;
         int m_t, n_t, sp;
-        decode_work(p, worker, m_t, n_t, sp);
+        decode_work(p, w, m_t, n_t, sp);
         if (CG == 2) m_t = m_t * 2 + (int)cta_rank;
-        issue_aux(m_t, n_t, 0);
+        const int slot = (int)(seq % NAUX);
+        mbar_expect_tx(&aux_full_bar[2 * grp + slot], EPI_BUF_BYTES);
+        tma_load_2d(tile2 + slot * EPI_BUF_BYTES, &tmap_out2, &aux_full_bar[2 * grp + slot],
+                    n_t * BN + (grp + 2 * rd) * CW, m_t * BM);
+      };
+      if (AUX && et == 0) {
+        for (int a = 0; a < NAUX; ++a) issue_aux(worker, 0, a, (uint32_t)a);
       }
       for (int w = worker; w < total_work; w += n_workers) {
         int m_tile, n_tile, split;
@@ -477,120 +493,122 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll 1
         for (int rd = 0; rd < ROUNDS; ++rd) {
           const int cc = (grp + 2 * rd) * CW;        // first column of the round inside the tile
-          uint32_t r[CW];
-          tmem_ld_32x32_at<0>(taddr + cc, r);
-          if (CW == 64) tmem_ld_32x32_at<(CW == 64 ? 32 : 0)>(taddr + cc + 32, r);
-          uint32_t ax[AUX ? 32 : 1];                 // aux row: 64 bf16 (DGELU) or 32 fp32 (RESID)
-          if (AUX) {
-            mbar_wait(&aux_full_bar[grp], aux_phase);
+          const int aslot = (int)(aux_seq % NAUX);
+          const uint32_t aphase = (aux_seq / NAUX) & 1u;
+          if (AUX) mbar_wait(&aux_full_bar[2 * grp + aslot], aphase);
+#pragma unroll 1      // (rolled: the unrolled round was 670 instructions, and 6 % of the epilogue's samples were i-cache misses)
+          for (int hf = 0; hf < HALVES; ++hf) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + cc + 32 * hf, r);
+            // aux of these 32 columns: 32 bf16 = 4 pieces (DGELU) or 32 fp32 = 8 pieces (RESID)
+            constexpr int AXP = OUT_F32 ? 8 : 4;
+            uint32_t ax[AUX ? 4 * AXP : 1];
+            if (AUX) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 t4 = lds128(auxp + ((j ^ swz) << 4));
-              ax[AUX ? 4 * j : 0] = t4.x; ax[AUX ? 4 * j + 1 : 0] = t4.y; ax[AUX ? 4 * j + 2 : 0] = t4.z; ax[AUX ? 4 * j + 3 : 0] = t4.w;
-            }
-            mbar_arrive(&aux_free_bar[grp]);
-            if (et == 0) {
-              // refill the aux tile for the next round of this group (possibly the next tile) as soon as all have read it
-              mbar_wait(&aux_free_bar[grp], aux_phase);
-              if (rd + 1 < ROUNDS) {
-                issue_aux(m_tile, n_tile, rd + 1);
-              } else if (w + n_workers < total_work) {
-                int m_t, n_t, sp;
-                decode_work(p, w + n_workers, m_t, n_t, sp);
-                if (CG == 2) m_t = m_t * 2 + (int)cta_rank;
-                issue_aux(m_t, n_t, 0);
+              for (int j = 0; j < AXP; ++j) {
+                const uint4 t4 = lds128(row2p + aslot * EPI_BUF_BYTES + (((AXP * hf + j) ^ swz) << 4));
+                ax[AUX ? 4 * j : 0] = t4.x; ax[AUX ? 4 * j + 1 : 0] = t4.y; ax[AUX ? 4 * j + 2 : 0] = t4.z; ax[AUX ? 4 * j + 3 : 0] = t4.w;
+              }
+              if (hf == HALVES - 1) {
+                mbar_arrive(&aux_free_bar[2 * grp + aslot]);
+                if (et == 0) {
+                  // refill this aux tile for the round NAUX rounds ahead (possibly of a later tile) once all have read it
+                  mbar_wait(&aux_free_bar[2 * grp + aslot], aphase);
+                  issue_aux(w, rd, NAUX, aux_seq);
+                }
+                ++aux_seq;
               }
             }
-            aux_phase ^= 1;
-          }
-          tmem_ld_wait();
-          if (rd == ROUNDS - 1) {          // last TMEM read of this accumulator stage: hand it back to the MMA warp
-            tc_fence_before();
-            if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
-            else mbar_arrive(&tmem_empty_bar[acc]);
-          }
-          uint32_t o[OUT_F32 ? CW : CW / 2];
-          uint32_t o2[EPI == B200_EPI_GELU_BF16 ? CW / 2 : 1];
+            tmem_ld_wait();
+            if (rd == ROUNDS - 1 && hf == HALVES - 1) {   // last TMEM read of this accumulator stage: hand it back
+              tc_fence_before();
+              if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            uint32_t o[OUT_F32 ? 32 : 16];
+            uint32_t o2[TWO_OUT ? 16 : 1];
 #pragma unroll
-          for (int q = 0; q < CW / 4; ++q) {
-            f32x2 v01 = f2_pack(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]));
-            f32x2 v23 = f2_pack(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-            if (p.bias != nullptr) {
-              const uint4 bq = lds128(sbias_s + (rd * CW + 4 * q) * 4);      // same address in every lane: broadcast
-              v01 = f2_add(v01, f2_pack(__uint_as_float(bq.x), __uint_as_float(bq.y)));
-              v23 = f2_add(v23, f2_pack(__uint_as_float(bq.z), __uint_as_float(bq.w)));
-            }
-            f32x2 dm01 = f2_splat(0.f), dm23 = f2_splat(0.f);
-            const bool drop_on = (EPI != B200_EPI_STORE_BF16) && p.drop_threshold16 != 0u;
-            if (drop_on) {
-              const uint32_t pair = (uint32_t)(((long long)grow * p.N + (n_tile * BN + cc + 4 * q)) >> 1);
-              float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
-              dropout_pair(p.drop_seed, pair, p.drop_threshold16, drop_sc, d0, d1);
-              dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, drop_sc, d2, d3);
-              dm01 = f2_pack(d0, d1);
-              dm23 = f2_pack(d2, d3);
-              if (AUX) {                    // RESID drops (acc + bias), DGELU masks the incoming gradient
-                v01 = f2_mul(v01, dm01);
-                v23 = f2_mul(v23, dm23);
+            for (int q = 0; q < 8; ++q) {   // (fully unrolled: o[] / r[] must stay in registers)
+              f32x2 v01 = f2_pack(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]));
+              f32x2 v23 = f2_pack(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+              if (p.bias != nullptr) {
+                const uint4 bq = lds128(sbias_s + (rd * CW + 32 * hf + 4 * q) * 4);    // same address in every lane: broadcast
+                v01 = f2_add(v01, f2_pack(__uint_as_float(bq.x), __uint_as_float(bq.y)));
+                v23 = f2_add(v23, f2_pack(__uint_as_float(bq.z), __uint_as_float(bq.w)));
               }
-            }
-            float v0, v1, v2, v3;
-            if (EPI == B200_EPI_STORE_BF16) {
-              f2_unpack(v01, v0, v1);
-              f2_unpack(v23, v2, v3);
-              o[2 * q] = pack_bf16(v0, v1);
-              o[2 * q + 1] = pack_bf16(v2, v3);
-            } else if (EPI == B200_EPI_GELU_BF16) {
-              // out2 = pre-activation h (bf16); out = gelu(h) evaluated on the ROUNDED h (what autocast feeds nn.GELU)
-              f2_unpack(v01, v0, v1);
-              f2_unpack(v23, v2, v3);
-              const uint32_t h01 = pack_bf16(v0, v1), h23 = pack_bf16(v2, v3);
-              o2[EPI == B200_EPI_GELU_BF16 ? 2 * q : 0] = h01;
-              o2[EPI == B200_EPI_GELU_BF16 ? 2 * q + 1 : 0] = h23;
-              f32x2 g01 = gelu_erf2(f2_pack(bf16_lo(h01), bf16_hi(h01)));
-              f32x2 g23 = gelu_erf2(f2_pack(bf16_lo(h23), bf16_hi(h23)));
+              f32x2 dm01 = f2_splat(0.f), dm23 = f2_splat(0.f);
+              constexpr bool drop_on = DROP;
               if (drop_on) {
-                g01 = f2_mul(g01, dm01);
-                g23 = f2_mul(g23, dm23);
+                const uint32_t pair = (uint32_t)(((long long)grow * p.N + (n_tile * BN + cc + 32 * hf + 4 * q)) >> 1);
+                float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
+                dropout_pair(p.drop_seed, pair, p.drop_threshold16, drop_sc, d0, d1);
+                dropout_pair(p.drop_seed, pair + 1, p.drop_threshold16, drop_sc, d2, d3);
+                dm01 = f2_pack(d0, d1);
+                dm23 = f2_pack(d2, d3);
+                if (AUX) {                    // RESID drops (acc + bias), DGELU masks the incoming gradient
+                  v01 = f2_mul(v01, dm01);
+                  v23 = f2_mul(v23, dm23);
+                }
               }
-              f2_unpack(g01, v0, v1);
-              f2_unpack(g23, v2, v3);
-              o[2 * q] = pack_bf16(v0, v1);
-              o[2 * q + 1] = pack_bf16(v2, v3);
-            } else if (EPI == B200_EPI_DGELU_BF16) {
-              // out = acc * gelu'(h), h = saved bf16 pre-activation (aux)
-              const uint32_t h01 = ax[AUX ? 2 * q : 0], h23 = ax[AUX ? 2 * q + 1 : 0];
-              f2_unpack(f2_mul(v01, gelu_erf_grad2(f2_pack(bf16_lo(h01), bf16_hi(h01)))), v0, v1);
-              f2_unpack(f2_mul(v23, gelu_erf_grad2(f2_pack(bf16_lo(h23), bf16_hi(h23)))), v2, v3);
-              o[2 * q] = pack_bf16(v0, v1);
-              o[2 * q + 1] = pack_bf16(v2, v3);
-            } else {
-              // RESID: out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
-              f2_unpack(f2_add(v01, f2_pack(__uint_as_float(ax[AUX ? 4 * q : 0]), __uint_as_float(ax[AUX ? 4 * q + 1 : 0]))), v0, v1);
-              f2_unpack(f2_add(v23, f2_pack(__uint_as_float(ax[AUX ? 4 * q + 2 : 0]), __uint_as_float(ax[AUX ? 4 * q + 3 : 0]))), v2, v3);
-              o[OUT_F32 ? 4 * q : 0] = __float_as_uint(v0);
-              o[OUT_F32 ? 4 * q + 1 : 0] = __float_as_uint(v1);
-              o[OUT_F32 ? 4 * q + 2 : 0] = __float_as_uint(v2);
-              o[OUT_F32 ? 4 * q + 3 : 0] = __float_as_uint(v3);
+              float v0, v1, v2, v3;
+              if (EPI == B200_EPI_STORE_BF16) {
+                f2_unpack(v01, v0, v1);
+                f2_unpack(v23, v2, v3);
+                o[2 * q] = pack_bf16(v0, v1);
+                o[2 * q + 1] = pack_bf16(v2, v3);
+              } else if (EPI == B200_EPI_GELU_BF16) {
+                // out2 = pre-activation h (bf16); out = gelu(h) evaluated on the ROUNDED h (what autocast feeds nn.GELU)
+                f2_unpack(v01, v0, v1);
+                f2_unpack(v23, v2, v3);
+                const uint32_t h01 = pack_bf16(v0, v1), h23 = pack_bf16(v2, v3);
+                o2[TWO_OUT ? 2 * q : 0] = h01;
+                o2[TWO_OUT ? 2 * q + 1 : 0] = h23;
+                f32x2 g01 = gelu_erf2(f2_pack(bf16_lo(h01), bf16_hi(h01)));
+                f32x2 g23 = gelu_erf2(f2_pack(bf16_lo(h23), bf16_hi(h23)));
+                if (drop_on) {
+                  g01 = f2_mul(g01, dm01);
+                  g23 = f2_mul(g23, dm23);
+                }
+                f2_unpack(g01, v0, v1);
+                f2_unpack(g23, v2, v3);
+                o[2 * q] = pack_bf16(v0, v1);
+                o[2 * q + 1] = pack_bf16(v2, v3);
+              } else if (EPI == B200_EPI_DGELU_BF16) {
+                // out = acc * gelu'(h), h = saved bf16 pre-activation (aux)
+                const uint32_t h01 = ax[AUX ? 2 * q : 0], h23 = ax[AUX ? 2 * q + 1 : 0];
+                f2_unpack(f2_mul(v01, gelu_erf_grad2(f2_pack(bf16_lo(h01), bf16_hi(h01)))), v0, v1);
+                f2_unpack(f2_mul(v23, gelu_erf_grad2(f2_pack(bf16_lo(h23), bf16_hi(h23)))), v2, v3);
+                o[2 * q] = pack_bf16(v0, v1);
+                o[2 * q + 1] = pack_bf16(v2, v3);
+              } else {
+                // RESID: out(fp32) = aux(fp32 residual) + acc + bias ; out may alias aux
+                f2_unpack(f2_add(v01, f2_pack(__uint_as_float(ax[OUT_F32 ? 4 * q : 0]), __uint_as_float(ax[OUT_F32 ? 4 * q + 1 : 0]))), v0, v1);
+                f2_unpack(f2_add(v23, f2_pack(__uint_as_float(ax[OUT_F32 ? 4 * q + 2 : 0]), __uint_as_float(ax[OUT_F32 ? 4 * q + 3 : 0]))), v2, v3);
+                o[OUT_F32 ? 4 * q : 0] = __float_as_uint(v0);
+                o[OUT_F32 ? 4 * q + 1 : 0] = __float_as_uint(v1);
+                o[OUT_F32 ? 4 * q + 2 : 0] = __float_as_uint(v2);
+                o[OUT_F32 ? 4 * q + 3 : 0] = __float_as_uint(v3);
+              }
             }
-          }
-          // the staging tile(s) must be free: the previous round's bulk store has finished reading them
-          if (et == 0) tma_wait_group_read<0>();
-          named_bar_sync(bar_id, 128);
-          constexpr int PIECES = (EPI == B200_EPI_GELU_BF16) ? 4 : 8;     // 16-byte pieces per staged row
+            if (hf == 0) {
+              // the staging tile(s) must be free: the previous round's bulk store has finished reading them
+              if (et == 0) tma_wait_group_read<0>();
+              named_bar_sync(bar_id, 128);
+            }
+            constexpr int PIECES = OUT_F32 ? 8 : 4;      // 16-byte pieces this half contributes to the staged row
 #pragma unroll
-          for (int j = 0; j < PIECES; ++j) {
-            sts128(rowp + ((j ^ swz) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            if (EPI == B200_EPI_GELU_BF16)
-              sts128(rowp + EPI_BUF_BYTES / 2 + ((j ^ swz) << 4), o2[EPI == B200_EPI_GELU_BF16 ? 4 * j : 0],
-                     o2[EPI == B200_EPI_GELU_BF16 ? 4 * j + 1 : 0], o2[EPI == B200_EPI_GELU_BF16 ? 4 * j + 2 : 0],
-                     o2[EPI == B200_EPI_GELU_BF16 ? 4 * j + 3 : 0]);
+            for (int j = 0; j < PIECES; ++j) {
+              sts128(rowp + (((PIECES * hf + j) ^ swz) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              if (TWO_OUT)
+                sts128(row2p + (((PIECES * hf + j) ^ swz) << 4), o2[TWO_OUT ? 4 * j : 0], o2[TWO_OUT ? 4 * j + 1 : 0],
+                       o2[TWO_OUT ? 4 * j + 2 : 0], o2[TWO_OUT ? 4 * j + 3 : 0]);
+            }
           }
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
           if (et == 0 && n_tile * BN + cc < p.N) {
             tma_store_2d(&tmap_out, buf, n_tile * BN + cc, m_tile * BM);
-            if (EPI == B200_EPI_GELU_BF16) tma_store_2d(&tmap_out2, buf + EPI_BUF_BYTES / 2, n_tile * BN + cc, m_tile * BM);
+            if (TWO_OUT) tma_store_2d(&tmap_out2, tile2, n_tile * BN + cc, m_tile * BM);
             tma_commit_group();
           }
         }
@@ -648,8 +666,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         } else {
           named_bar_sync(bar_id, 128);
           // phase 2: coalesced pass. thread -> (row = et/8 + 16*i, 4 columns at (et%8)*4)
-          if (interior) epilogue_rows<EPI, true>(p, buf_s, et, row0, col, aux);
-          else epilogue_rows<EPI, false>(p, buf_s, et, row0, col, aux);
+          if (interior) epilogue_rows<EPI, true, DROP>(p, buf_s, et, row0, col, aux);
+          else epilogue_rows<EPI, false, DROP>(p, buf_s, et, row0, col, aux);
         }
       }
       if (++acc == 2) {
@@ -675,10 +693,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI, int CG>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP>
 static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                           const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG, DROP>;
   constexpr int SMEM = GemmCfg<BN, CG, EPI>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
@@ -713,8 +731,13 @@ static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                        const GemmParams& p, int grid, bool cta_pairs, cudaStream_t stream) {
-  if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2>(ta, tb, to, to2, p, grid, stream);
-  return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1>(ta, tb, to, to2, p, grid, stream);
+  constexpr bool CAN_DROP = EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16;
+  if (CAN_DROP && p.drop_threshold16 != 0u) {
+    if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP>(ta, tb, to, to2, p, grid, stream);
+    return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, CAN_DROP>(ta, tb, to, to2, p, grid, stream);
+  }
+  if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false>(ta, tb, to, to2, p, grid, stream);
+  return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, false>(ta, tb, to, to2, p, grid, stream);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -796,10 +819,8 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   B200_CHECK_ARG(BN == 128 || BN == 256, "b200_gemm_bf16: block_n must be 128 or 256");
 
   // CTA pairs (256-row tiles) whenever the wide tile is used and there are at least two 128-row tiles
-  // (measured at the train-step shapes: STORE -13 %, wgrad -6 %; the GELU / DGELU / RESID epilogues are bound by their
-  //  own epilogue warps, and coupling two of them behind one accumulator hand-back costs 1-4 %, so they stay single)
-  const bool pair_epi = epilogue == B200_EPI_STORE_BF16 || epilogue == B200_EPI_STORE_F32 || epilogue == B200_EPI_REDUCE_F32;
-  const bool cta_pairs = (BN == 256) && (M > BM) && (g_force_single_cta != 1) && (pair_epi || g_force_single_cta == -1);
+  // (measured at the train-step shapes, pairs vs single CTAs: STORE -17 %, wgrad -6 %, GELU -14 %, DGELU -7 %, RESID -4 %)
+  const bool cta_pairs = (BN == 256) && (M > BM) && (g_force_single_cta != 1);
   const int tile_m = cta_pairs ? 2 * BM : BM;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -896,12 +917,12 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
     }
     if (epilogue == B200_EPI_GELU_BF16 && ldo % 8 == 0 && ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(out2) & 15) == 0) {
-      dims[0] = (uint64_t)N; dims[1] = (uint64_t)M; box[0] = 32; box[1] = BM;
+      dims[0] = (uint64_t)N; dims[1] = (uint64_t)M; box[0] = 64; box[1] = BM;
       strides[0] = (uint64_t)ldo * 2;
-      rc = make_tmap(&to, out, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_64B);
+      rc = make_tmap(&to, out, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
       if (rc) return rc;
       strides[0] = (uint64_t)ldo2 * 2;
-      rc = make_tmap(&to2, out2, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_64B);
+      rc = make_tmap(&to2, out2, TMA_BF16, 2, dims, strides, box, TMA_SWIZZLE_128B);
       if (rc) return rc;
       p.tma_epi = 1;
     }
