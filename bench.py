@@ -248,9 +248,29 @@ def run_b200_arm(args):
     gemm_ms, gemm_flops, gemm_n = prof["b200_gemm_bf16"]["ms"], prof["b200_gemm_bf16"]["flops"], prof["b200_gemm_bf16"]["calls"]
     att_ms = prof["b200_attention_fwd"]["ms"] + prof["b200_attention_bwd"]["ms"]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM traffic per launch from the committed ncu --set full captures (profiles/), weighted by this step's call mix
+    traffic, traffic_detail = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_dram_traffic.json")) as fh:
+            cap = json.load(fh)["variants"]
+        tot_b, tot_c = 0.0, 0
+        traffic_detail = {}
+        for tag, det in prof["b200_gemm_bf16"]["detail"].items():
+            if tag in cap:
+                b = cap[tag]["dram_read_bytes"] + cap[tag]["dram_write_bytes"]
+                traffic_detail[tag] = {"dram_bytes_per_launch": b, "algorithmic_bytes": cap[tag]["algorithmic_bytes"],
+                                       "shape": cap[tag]["shape"]}
+                tot_b += b * det["calls"]
+                tot_c += det["calls"]
+        if tot_c:
+            traffic = tot_b / tot_c
+            traffic_detail["note"] = ("mean DRAM bytes per launch over the captured variants (each at its encoder shape), "
+                                      "weighted by calls per step; source profiles/r01_gemm_dram_traffic.json")
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05, all layouts/epilogues)", "achieved": achieved,
                 "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "launches_per_step": gemm_n, "gemm_ms_per_step": gemm_ms, "attention_ms_per_step": att_ms,
                 "share_of_step": gemm_ms / ms_step,
                 "by_variant": prof["b200_gemm_bf16"]["detail"],
