@@ -27,7 +27,7 @@ constexpr int AB_THREADS = (AB_MMA_WARP + 1) * 32;    // 448 threads -> 128 regi
 constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB bf16 tile
 constexpr int AB_SMEM = 12 * AB_TILE + 256 + 1024;   // K, V, Q[2], dO[2], P(2), dS(2), dQ staging(2) = 192 KB
 
-constexpr uint32_t TB_S = 0, TB_DP = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384;
+constexpr uint32_t TB_S = 0, TB_DP = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384, TB_DS = 448;   // TB_DS: dS as bf16 pairs
 
 #ifdef AB_TRACE
 #define AB_STAMP(slot)                                                                     \
@@ -220,8 +220,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         AB_STAMP(11);
         tc_fence_after();
         // dS read K-major for dQ: 64-key chunk = k / 4, 32 bytes per step inside the 128-byte row
-        const uint64_t dS_k0 = make_smem_desc(smem_u32(sdS), 16, 1024);
-        const uint64_t dS_k1 = make_smem_desc(smem_u32(sdS + AB_TILE), 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -237,8 +235,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_ss(tmem_base + TB_DQ, (k < 4 ? dS_k0 : dS_k1) + (uint64_t)(2 * (k & 3)), dK_mn + (uint64_t)(128 * k),
-                    idesc_q, k > 0 ? 1u : 0u);
+            umma_ts(tmem_base + TB_DQ, tmem_base + TB_DS + 8 * k, dK_mn + (uint64_t)(128 * k), idesc_q, k > 0 ? 1u : 0u);
           umma_commit(dq_full);
         }
         __syncwarp();
@@ -397,14 +394,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const f32x2 ps = f2_mul(f2_pack(bf16_lo(w), bf16_hi(w)), scale2);
             f2_unpack(f2_mul(f2_add(g, ndsum2), ps), dsv[e], dsv[e + 1]);
           }
+          uint32_t dw[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) dw[e] = pack_bf16(dsv[2 * e], dsv[2 * e + 1]);
+          // dS goes to shared memory (MN-major A operand of dK += dS^T Q) AND to TMEM: there it is already laid out as the
+          // A operand of dQ = dS K (lane = query, columns = keys), and an MMA with A in TMEM costs 52 instead of 76 cycles
+          tmem_st_32x16(lane_addr + TB_DS + half * 32 + c * 16, dw);
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int piece = (c * 4 + jj) ^ sw;
-            sts128(drow + (piece << 4), pack_bf16(dsv[8 * jj], dsv[8 * jj + 1]), pack_bf16(dsv[8 * jj + 2], dsv[8 * jj + 3]),
-                   pack_bf16(dsv[8 * jj + 4], dsv[8 * jj + 5]), pack_bf16(dsv[8 * jj + 6], dsv[8 * jj + 7]));
+            sts128(drow + (piece << 4), dw[4 * jj], dw[4 * jj + 1], dw[4 * jj + 2], dw[4 * jj + 3]);
           }
         }
       }
+      tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
