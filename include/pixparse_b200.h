@@ -176,6 +176,10 @@ int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo,
 /* Bring-up / A-B switch: on = 1 makes b200_gemm_bf16 use one CTA per 128-row tile everywhere instead of CTA pairs
  * (tcgen05 cta_group::2, 256-row tiles) for the 256-column tile width. Results are identical either way. */
 int b200_debug_gemm_single_cta(int on);
+/* Kernel selection for b200_attention_bwd without dropout: on = 1 (default) query-major accumulators (the kernel the
+ * dropout variant always uses), on = 0 key-major accumulators (P^T / dS^T fed to the dV / dK MMAs from tensor memory).
+ * Results agree to bf16 rounding; the two are on par on B200 (profiles/), the switch exists for A-B runs. */
+int b200_debug_attention_bwd_query_major(int on);
 
 #ifdef __cplusplus
 }

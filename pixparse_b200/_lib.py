@@ -35,6 +35,11 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.b200_last_error.restype = ctypes.c_char_p
         _declare(_lib)
+        # A/B switches for bring-up (scripts/gpu_ab.sh): kernel selection only, results are equivalent
+        if os.environ.get("PIXPARSE_B200_ATTN_BWD_QUERY_MAJOR"):
+            _lib.b200_debug_attention_bwd_query_major(int(os.environ["PIXPARSE_B200_ATTN_BWD_QUERY_MAJOR"]))
+        if os.environ.get("PIXPARSE_B200_GEMM_SINGLE_CTA"):
+            _lib.b200_debug_gemm_single_cta(int(os.environ["PIXPARSE_B200_GEMM_SINGLE_CTA"]))
     return _lib
 
 
@@ -50,6 +55,7 @@ SIGNATURES = {
     "b200_device_check": [],
     "b200_debug_gemm_desc": [_I, _I, _I, _I, _I, _I],
     "b200_debug_gemm_single_cta": [_I],
+    "b200_debug_attention_bwd_query_major": [_I],
     "b200_attention_fwd": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "b200_attention_fwd_strided": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I,
                                    _F, _P],

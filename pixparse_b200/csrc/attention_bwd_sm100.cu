@@ -10,7 +10,7 @@
 // exactly as TMA delivers them (K-major for S / dP, MN-major for dV / dK / dQ).
 //
 // Replaces the SDPA backward kernels autograd reaches from timm Attention and BartAttention.
-#include "common.cuh"
+#include "attention_bwd_common.cuh"
 #include "../../include/pixparse_b200.h"
 
 namespace b200 {
@@ -18,37 +18,6 @@ namespace b200 {
 int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long width, long long ld, int box_rows,
                   long long batch_stride);
 
-constexpr int AB_T = 128;                 // tile edge (queries and keys)
-constexpr int AB_D = 64;
-constexpr int AB_COMPUTE_THREADS = 256;   // warps 0-7: warp w owns query rows 32*(w%4).., key columns 64*(w/4)..
-constexpr int AB_DRAIN_WARP0 = 8;         // warps 8-11: dQ_t TMEM -> shared -> TMA reduce-add, off the compute warps' path
-constexpr int AB_TMA_WARP = 12, AB_MMA_WARP = 13;
-constexpr int AB_THREADS = (AB_MMA_WARP + 1) * 32;    // 448 threads -> 128 registers per thread
-constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB bf16 tile
-constexpr int AB_SMEM = 12 * AB_TILE + 256 + 1024;   // K, V, Q[2], dO[2], P(2), dS(2), dQ staging(2) = 192 KB
-
-constexpr uint32_t TB_S = 0, TB_DP = 128, TB_DV = 256, TB_DK = 320, TB_DQ = 384, TB_DS = 448;   // TB_DS: dS as bf16 pairs
-
-#ifdef AB_TRACE
-#define AB_STAMP(slot)                                                                     \
-  do {                                                                                     \
-    if (trace_on && t < 8) p.trace[(t * 16 + (slot))] = clock64();                         \
-  } while (0)
-#else
-#define AB_STAMP(slot) do { } while (0)
-#endif
-
-struct AttBwdParams {
-  int B, H, Sq, Sk, causal;
-  float scale, scale_log2;
-  const float* lse;      // [B, H, Sq]
-  const float* dsum;     // [B, H, Sq]  rowsum(dO * O)
-  bf16* dk; long long ld_dk; int dk_col0;
-  bf16* dv; long long ld_dv; int dv_col0;
-  int q_col0, k_col0, v_col0, do_col0;
-  uint32_t drop_threshold16, drop_seed;   // attention-probability dropout of the forward pass (0 = off)
-  long long* trace;                       // bring-up builds only (-DAB_TRACE): clock64 stamps of CTA (3,0,0)
-};
 
 // Pipeline per query tile t (tensor pipe on the left, the 8 compute warps on the right run concurrently):
 //     S_t, dP_t ready ............ stage A: P_t = exp2(S_t*c - LSE)  -> smem, keeps P_t in registers
@@ -453,9 +422,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 // D[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (8 threads x 16 bytes per (b,q,h) row of 64 elements; coalesced)
+// Also writes the padded per-(b, h) copies the key-major kernel reads with unpredicated 16-byte loads:
+// lse2_pad = LSE * log2(e) (+inf beyond Sq -> P = 0 for padded queries), dsum_pad (0 beyond Sq).
+__global__ void attention_bwd_pad_kernel(float* __restrict__ lse2_pad, float* __restrict__ dsum_pad, int BH, int Sq,
+                                         int Sq_pad) {
+  const int npad = Sq_pad - Sq;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BH * npad; i += gridDim.x * blockDim.x) {
+    const int bh = i / npad, q = Sq + i % npad;
+    lse2_pad[(long long)bh * Sq_pad + q] = INFINITY;
+    dsum_pad[(long long)bh * Sq_pad + q] = 0.f;
+  }
+}
 __global__ void attention_bwd_prep_kernel(const bf16* __restrict__ o, long long ld_o, const bf16* __restrict__ d_o,
                                           long long ld_do, int do_col0, float* __restrict__ dsum, int B, int H,
-                                          int Sq) {
+                                          int Sq, const float* __restrict__ lse, float* __restrict__ lse2_pad,
+                                          float* __restrict__ dsum_pad, int Sq_pad) {
   const long long total = (long long)B * Sq * H * 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {      // total and the stride are multiples of 8: groups stay intact
@@ -475,6 +456,9 @@ __global__ void attention_bwd_prep_kernel(const bf16* __restrict__ o, long long 
     if (part == 0) {
       const int bb = (int)(bq / Sq), q = (int)(bq % Sq);
       dsum[((long long)bb * H + hh) * Sq + q] = s;
+      const long long ip = ((long long)bb * H + hh) * Sq_pad + q;
+      dsum_pad[ip] = s;
+      lse2_pad[ip] = lse[((long long)bb * H + hh) * Sq + q] * 1.4426950408889634f;
     }
   }
 }
@@ -502,9 +486,18 @@ long long* g_ab_trace = nullptr;
 extern "C" int b200_debug_set_trace(long long* ptr) { g_ab_trace = ptr; return 0; }
 #endif
 
+// kernel selection for the no-dropout case: 1 = query-major (default), 0 = key-major (attention_bwd_kt_sm100.cu)
+static int g_ab_query_major = 1;      // measured in the full step: query-major 0.3 % ahead of key-major, standalone on par
+extern "C" int b200_debug_attention_bwd_query_major(int on) {
+  g_ab_query_major = on;
+  return 0;
+}
+
 extern "C" long long b200_attention_bwd_workspace_bytes(int B, int H, int Sq) {
-  // fp32 dQ accumulator [B*Sq, H*64] followed by D [B, H, Sq]
-  return ((long long)B * Sq * H * 64 + (long long)B * H * Sq) * 4;
+  // fp32 dQ accumulator [B*Sq, H*64], D [B, H, Sq], then the padded LSE*log2e and D [B, H, Sq_pad] (each 16-byte aligned)
+  const long long sq_pad = (Sq + 127) / 128 * 128;
+  const long long head = (((long long)B * Sq * H * 64 + (long long)B * H * Sq) + 3) / 4 * 4;
+  return (head + 2 * (long long)B * H * sq_pad) * 4;
 }
 
 static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
@@ -556,6 +549,10 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
   const int W = H * AB_D;
   float* dq32 = reinterpret_cast<float*>(workspace);
   float* dsum = dq32 + (long long)B * Sq * W;
+  const int Sq_pad = (Sq + AB_T - 1) / AB_T * AB_T;
+  float* lse2_pad = dq32 + (((long long)B * Sq * W + (long long)B * H * Sq) + 3) / 4 * 4;
+  float* dsum_pad = lse2_pad + (long long)B * H * Sq_pad;
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "b200_attention_bwd: workspace must be 16-byte aligned");
   cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * Sq * W * 4, s);
   if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(dq32)");
 
@@ -564,9 +561,13 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
     long long blocks = (items + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
+    if (Sq_pad > Sq) {
+      attention_bwd_pad_kernel<<<(B * H * (Sq_pad - Sq) + 255) / 256, 256, 0, s>>>(lse2_pad, dsum_pad, B * H, Sq, Sq_pad);
+      B200_CHECK_LAUNCH("attention_bwd_pad");
+    }
     attention_bwd_prep_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(o), ld_o,
                                                          reinterpret_cast<const bf16*>(d_o), ld_do, do_col0, dsum, B,
-                                                         H, Sq);
+                                                         H, Sq, lse, lse2_pad, dsum_pad, Sq_pad);
     B200_CHECK_LAUNCH("attention_bwd_prep");
   }
 
@@ -587,6 +588,8 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
   p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse; p.dsum = dsum;
+  AttBwdPadded pp;
+  pp.lse2_pad = lse2_pad; pp.dsum_pad = dsum_pad; pp.Sq_pad = Sq_pad;
   p.dk = reinterpret_cast<bf16*>(dk); p.ld_dk = ld_dk; p.dk_col0 = dk_col0;
   p.dv = reinterpret_cast<bf16*>(dv); p.ld_dv = ld_dv; p.dv_col0 = dv_col0;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.do_col0 = do_col0;
@@ -602,12 +605,14 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
     e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attention_bwd)");
     configured = true;
   }
   dim3 grid((Sk + AB_T - 1) / AB_T, H, B);
   if (p.drop_threshold16 != 0u) attention_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
-  else attention_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
+  else if (g_ab_query_major) attention_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
+  else if ((rc = launch_attention_bwd_kt(tq, tk, tv, tdo, tdq, p, pp, grid, s))) return rc;
   B200_CHECK_LAUNCH("attention_bwd");
 
   {

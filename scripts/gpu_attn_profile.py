@@ -2,7 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pixparse_b200 import ops
+from pixparse_b200 import ops, _lib
+if os.environ.get("QUERY_MAJOR"):
+    _lib.lib().b200_debug_attention_bwd_query_major(1)
 B, H = 32, 12
 D = H * 64
 iters = int(os.environ.get("ITERS", "10"))
