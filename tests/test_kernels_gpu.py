@@ -117,7 +117,18 @@ def test_attention_fwd(cuda_lib, B, H, Sq, Sk, causal):
 @pytest.mark.parametrize("B,H,Sq,Sk,causal", [
     (2, 2, 128, 128, False), (1, 3, 1009, 1009, False), (2, 2, 512, 512, True), (2, 2, 200, 1009, False),
     (1, 2, 4, 300, False), (1, 2, 4, 4, True), (1, 1, 300, 300, True)])
-def test_attention_bwd(cuda_lib, B, H, Sq, Sk, causal):
+@pytest.mark.parametrize("query_major", [1, 0])
+def test_attention_bwd(cuda_lib, B, H, Sq, Sk, causal, query_major):
+    """Both no-dropout kernels: query-major (default) and key-major (P^T / dS^T as tensor-memory A operands)."""
+    from pixparse_b200 import ops, _lib
+    _lib.lib().b200_debug_attention_bwd_query_major(query_major)
+    try:
+        _attention_bwd_case(B, H, Sq, Sk, causal)
+    finally:
+        _lib.lib().b200_debug_attention_bwd_query_major(1)
+
+
+def _attention_bwd_case(B, H, Sq, Sk, causal):
     from pixparse_b200 import ops
     torch.manual_seed(11)
     D = H * 64
