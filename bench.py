@@ -129,7 +129,7 @@ def run_reference_arm(args):
                                    "oracle = restated timm ViT + installed transformers BART + torch AdamW"},
         "e2e": {"value": pps, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     return 0
 
 
@@ -308,17 +308,36 @@ def run_b200_arm(args):
                                 "sample": f"1 train step of 2 pages (of {B}), T=512, fp32, all host threads: "
                                           f"{sec:.1f} s (setup+step {time.perf_counter() - t0:.0f} s)"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(line):
+    """The one JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
-    # keep stdout to the single JSON line: some boxes export NCCL_DEBUG=VERSION, which makes NCCL print a banner there
+    # keep stdout to the single JSON line: NCCL prints its version banner to stdout at communicator creation on some
+    # boxes (NCCL_DEBUG exported by the environment), and libraries may do the same. Everything that writes to fd 1 is
+    # sent to stderr for the life of the process; the JSON line goes to the saved original stdout.
+    global _REAL_STDOUT
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
