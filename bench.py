@@ -225,7 +225,7 @@ def run_b200_arm(args):
     e0.record()
     for i in range(args.steps):
         task.train_step(host[i % n_rot])
-        _ = task.last_loss[1].item()          # device -> host read of the step's loss
+        _ = task.last_loss_value()            # device -> host read of the step's loss (pinned copy made right after the CE kernel)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps

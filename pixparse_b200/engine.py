@@ -522,6 +522,7 @@ class CrullerEngine:
         return d_enc32
 
     _grad_ready_hook = None
+    on_loss_ready = None        # optional callable(stats): invoked right after the CE kernel is enqueued (async loss read-back)
 
     # ------------------------------------------------------------------------------------------------ public API
     def encode_images(self, image):
@@ -585,6 +586,8 @@ class CrullerEngine:
         if tflat.dtype != torch.int64 or not tflat.is_contiguous():
             tflat = tflat.long().contiguous()
         stats = ops.cross_entropy(logits, tflat, st_d.V, dlogits=logits, grad_scale=grad_scale, stats=stats)
+        if self.on_loss_ready is not None:      # the loss exists here, two thirds of the step before its end
+            self.on_loss_ready(stats)
         d_enc32 = self.decoder_backward(st_d, logits)
         self.encoder_backward(st_e, d_enc32)
         return stats

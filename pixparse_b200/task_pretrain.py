@@ -123,6 +123,10 @@ class TaskCrullerPretrain(TaskTrain):
         self.engine = None
         self.reducer = None
         self.last_loss = None      # device tensor [n_valid, mean_loss] of the latest micro-step
+        self._copy_stream = None   # host batch -> device copies (train_step)
+        self._loss_stream = None   # asynchronous loss read-back (last_loss_value)
+        self._loss_host = None
+        self._loss_event = None
 
     # ------------------------------------------------------------------------------------------------------------
     def train_setup(self, num_batches_per_interval: int):
@@ -176,9 +180,25 @@ class TaskCrullerPretrain(TaskTrain):
         image_input, text_input, text_target = sample
         result = {}
         device = self.device_env.device
-        image_input = image_input.to(device, non_blocking=True)
-        text_input = text_input[:, :-1].to(device, non_blocking=True).contiguous()
-        text_target = text_target[:, 1:].to(device, non_blocking=True).contiguous()
+        if image_input.device.type == 'cpu' and image_input.is_pinned() and device.type == 'cuda':
+            # Host batch: copy on a side stream so the transfer runs under the tail of the previous step (the host
+            # thread is ahead of the GPU), then make the compute stream wait for it.
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=device)
+            main = torch.cuda.current_stream(device)
+            with torch.cuda.stream(self._copy_stream):
+                image_input = image_input.to(device, non_blocking=True)
+                text_input = text_input.to(device, non_blocking=True)
+                text_target = text_target.to(device, non_blocking=True)
+            main.wait_stream(self._copy_stream)
+            for t in (image_input, text_input, text_target):
+                t.record_stream(main)
+            text_input = text_input[:, :-1].contiguous()
+            text_target = text_target[:, 1:].contiguous()
+        else:
+            image_input = image_input.to(device, non_blocking=True)
+            text_input = text_input[:, :-1].to(device, non_blocking=True).contiguous()
+            text_target = text_target[:, 1:].to(device, non_blocking=True).contiguous()
 
         accum_steps = self.cfg.opt.grad_accum_steps
         need_update = (self.interval_batch_idx + 1) % accum_steps == 0
@@ -186,6 +206,8 @@ class TaskCrullerPretrain(TaskTrain):
         if self.reducer is not None:
             self.reducer.enabled = need_update      # == model.no_sync() on accumulation micro-steps
             self.reducer.begin()
+        if device.type == 'cuda' and self.engine.on_loss_ready is None:
+            self.engine.on_loss_ready = self._stage_loss_readback
         self.last_loss = self.engine.forward_backward(image_input, text_input, text_target,
                                                       grad_scale=1.0 / accum_steps)
         if self.reducer is not None:
@@ -204,9 +226,35 @@ class TaskCrullerPretrain(TaskTrain):
         if self.step % self.eval_frequency == 0 and self.monitor is not None:
             self.monitor.log_step(
                 'train', step_idx=self.step, step_end_idx=self.num_intervals * self.num_steps_per_interval,
-                interval=self.interval_idx, loss=self.last_loss[1].item() / accum_steps,
+                interval=self.interval_idx, loss=self.last_loss_value() / accum_steps,
                 lr=self.get_current_lr(), metrics=self.train_metrics, eval_data=None)
         return result
+
+    # ---- loss read-back without draining the step -------------------------------------------------------------
+    # The CE kernel produces [n_valid, mean_loss] after the forward pass; backward and the optimizer (two thirds of the
+    # step) do not change it. A side stream copies it to pinned memory as soon as it exists, so a host read of the
+    # step's loss (logging every step) waits for the forward pass only and the GPU keeps running.
+    def _stage_loss_readback(self, stats):
+        dev = stats.device
+        if self._loss_stream is None:
+            self._loss_stream = torch.cuda.Stream(device=dev)
+            self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self._loss_event = torch.cuda.Event()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._loss_stream):
+            self._loss_stream.wait_event(ready)
+            self._loss_host.copy_(stats, non_blocking=True)
+            self._loss_event.record(self._loss_stream)
+        stats.record_stream(self._loss_stream)
+
+    def last_loss_value(self):
+        """Mean loss of the last train_step as a Python float (device -> host read; waits for that step's forward pass,
+        not for its backward / optimizer)."""
+        if self._loss_event is None:
+            return float(self.last_loss[1].item())
+        self._loss_event.synchronize()
+        return float(self._loss_host[1])
 
     def eval_step(self, sample):
         pass

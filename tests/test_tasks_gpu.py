@@ -46,6 +46,8 @@ def test_pretrain_task_interval_loop(cuda_lib):
     assert task.get_current_lr() == pytest.approx(0.5e-3)
     vals = [l[1].item() for l in losses]
     assert vals[-1] < vals[0]
+    # the asynchronous read-back (pinned copy staged right after the CE kernel) returns the last step's loss
+    assert task.last_loss_value() == pytest.approx(vals[-1], rel=1e-6)
     assert not torch.equal(p0, task.model.image_encoder.trunk.blocks[0].mlp.fc1.weight.detach())
     sd = task.state_dict()
     assert set(sd) == {"model", "optimizer", "scheduler"}
