@@ -12,6 +12,11 @@ import torch.distributed as dist
 
 class GradReducer:
     def __init__(self, flat_grads, process_group=None, bucket_bytes=64 << 20):
+        # tuning knob: PIXPARSE_B200_REDUCE_BUCKET_MB=<n> (0 = one all-reduce of the whole arena after backward)
+        import os
+        env = os.environ.get("PIXPARSE_B200_REDUCE_BUCKET_MB")
+        if env is not None:
+            bucket_bytes = int(env) << 20 if int(env) > 0 else (1 << 62)
         self.flat = flat_grads
         self.group = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
