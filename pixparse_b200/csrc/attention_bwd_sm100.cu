@@ -436,7 +436,7 @@ __global__ void attention_bwd_pad_kernel(float* __restrict__ lse2_pad, float* __
 __global__ void attention_bwd_prep_kernel(const bf16* __restrict__ o, long long ld_o, const bf16* __restrict__ d_o,
                                           long long ld_do, int do_col0, float* __restrict__ dsum, int B, int H,
                                           int Sq, const float* __restrict__ lse, float* __restrict__ lse2_pad,
-                                          float* __restrict__ dsum_pad, int Sq_pad) {
+                                          float* __restrict__ dsum_pad, int Sq_pad, float* __restrict__ dq32) {
   const long long total = (long long)B * Sq * H * 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {      // total and the stride are multiples of 8: groups stay intact
@@ -444,6 +444,12 @@ __global__ void attention_bwd_prep_kernel(const bf16* __restrict__ o, long long 
     const long long w = idx >> 3;
     const int hh = (int)(w % H);
     const long long bq = w / H;     // b * Sq + q
+    // zero this (row, head)'s 64 floats of the fp32 dQ accumulator on the way (replaces a separate 50-100 MB memset)
+    {
+      float4* z = reinterpret_cast<float4*>(dq32 + (bq * H + hh) * 64 + part * 8);
+      z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const uint4 a = *reinterpret_cast<const uint4*>(o + bq * ld_o + hh * 64 + part * 8);
     const uint4 g = *reinterpret_cast<const uint4*>(d_o + bq * ld_do + do_col0 + hh * 64 + part * 8);
     float s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
@@ -553,8 +559,7 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
   float* lse2_pad = dq32 + (((long long)B * Sq * W + (long long)B * H * Sq) + 3) / 4 * 4;
   float* dsum_pad = lse2_pad + (long long)B * H * Sq_pad;
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "b200_attention_bwd: workspace must be 16-byte aligned");
-  cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)B * Sq * W * 4, s);
-  if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(dq32)");
+  cudaError_t e = cudaSuccess;      // (dq32 is zeroed by the prep kernel)
 
   {
     const long long items = (long long)B * Sq * H * 8;
@@ -567,7 +572,7 @@ static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const vo
     }
     attention_bwd_prep_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(o), ld_o,
                                                          reinterpret_cast<const bf16*>(d_o), ld_do, do_col0, dsum, B,
-                                                         H, Sq, lse, lse2_pad, dsum_pad, Sq_pad);
+                                                         H, Sq, lse, lse2_pad, dsum_pad, Sq_pad, dq32);
     B200_CHECK_LAUNCH("attention_bwd_prep");
   }
 
