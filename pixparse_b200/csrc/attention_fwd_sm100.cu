@@ -184,7 +184,82 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // is renormalised by an exact power of two (P, its sum, the running O and l), which moves the reference instead
       // of re-reading S. The result O / l and the logsumexp do not depend on the reference chosen.
       // (the dropout variant keeps the two-pass route throughout: its mask code needs the registers, 4 CTAs per SM)
-      const bool exact_pass = DROP || (j == 0) || __any_sync(0xffffffffu, m_run == -INFINITY);     // warp-uniform
+      bool exact_pass = DROP || (j == 0) || __any_sync(0xffffffffu, m_run == -INFINITY);     // warp-uniform
+      if (!DROP && !exact_pass) {
+        uint32_t pk[ATT_BN / 2];
+        float l_tile = 0.f, pmax = 0.f;
+        auto single = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
+#pragma unroll
+          for (int c = 0; c < ATT_BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(lane_addr + TM_S + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_run));
+              float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_run));
+              if (MASKED) {
+                if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
+                if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
+              }
+              pmax = fmaxf(pmax, fmaxf(p0, p1));
+              l_tile += p0 + p1;        // the softmax normaliser uses the un-dropped probabilities
+              if (DROP)
+                dropout_pair(p.drop_seed, drop_row + (uint32_t)((k0 + c * 32 + 2 * e) >> 1), p.drop_threshold16, drop_sc,
+                             p0, p1);
+              pk[c * 16 + e] = pack_bf16(p0, p1);
+            }
+          }
+        };
+        if (need_mask) single(std::true_type{}); else single(std::false_type{});
+        if (__any_sync(0xffffffffu, !(pmax <= 1.8446744e19f))) {
+          // some row jumped by more than 2^64 against its reference (or overflowed to inf): nothing has been written
+          // yet, S is intact in TMEM, so this tile is simply redone on the exact two-pass route
+          exact_pass = true;
+        } else {
+          // exact power-of-two renormalisation of this row when the reference is more than 2^16 too small
+          float alpha = 1.0f;
+          if (pmax > 65536.0f) {
+            const int kexp = (int)((__float_as_uint(pmax) >> 23) & 0xffu) - 127;      // floor(log2(pmax))
+            alpha = __uint_as_float((uint32_t)(127 - kexp) << 23);                   // 2^-kexp
+  #pragma unroll
+            for (int e = 0; e < ATT_BN / 2; ++e) pk[e] = pack_bf16(bf16_lo(pk[e]) * alpha, bf16_hi(pk[e]) * alpha);
+            l_tile *= alpha;
+            m_run += (float)kexp;
+          }
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+  #pragma unroll 1
+            for (int c = 0; c < ATT_D / 32; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32(lane_addr + TM_O + c * 32, r);
+              tmem_ld_wait();
+  #pragma unroll
+              for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+              uint32_t lo[16], hi[16];
+  #pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                lo[e] = r[e];
+                hi[e] = r[16 + e];
+              }
+              tmem_st_32x16(lane_addr + TM_O + c * 32, lo);
+              tmem_st_32x16(lane_addr + TM_O + c * 32 + 16, hi);
+            }
+          }
+  #pragma unroll
+          for (int c = 0; c < ATT_BN / 32; ++c) {
+            uint32_t w16[16];
+  #pragma unroll
+            for (int e = 0; e < 16; ++e) w16[e] = pk[c * 16 + e];
+            tmem_st_32x16(lane_addr + TM_P + c * 16, w16);
+          }
+          tmem_st_wait();
+          l_run = l_run * alpha + l_tile;
+      
+        }
+      }
       if (exact_pass) {
         // ---- pass 1: row max
         float mx = -INFINITY;
@@ -260,73 +335,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tmem_st_wait();
         l_run = l_run * alpha + l_tile;
         m_run = m_new;
-      } else if (!DROP) {
-        uint32_t pk[ATT_BN / 2];
-        float l_tile = 0.f, pmax = 0.f;
-        auto single = [&](auto masked_tag) {
-          constexpr bool MASKED = decltype(masked_tag)::value;
-#pragma unroll
-          for (int c = 0; c < ATT_BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(lane_addr + TM_S + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_run));
-              float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_run));
-              if (MASKED) {
-                if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
-                if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
-              }
-              pmax = fmaxf(pmax, fmaxf(p0, p1));
-              l_tile += p0 + p1;        // the softmax normaliser uses the un-dropped probabilities
-              if (DROP)
-                dropout_pair(p.drop_seed, drop_row + (uint32_t)((k0 + c * 32 + 2 * e) >> 1), p.drop_threshold16, drop_sc,
-                             p0, p1);
-              pk[c * 16 + e] = pack_bf16(p0, p1);
-            }
-          }
-        };
-        if (need_mask) single(std::true_type{}); else single(std::false_type{});
-        // exact power-of-two renormalisation of this row when the reference is more than 2^16 too small
-        float alpha = 1.0f;
-        if (pmax > 65536.0f) {
-          const int kexp = (int)((__float_as_uint(pmax) >> 23) & 0xffu) - 127;      // floor(log2(pmax))
-          alpha = __uint_as_float((uint32_t)(127 - kexp) << 23);                   // 2^-kexp
-#pragma unroll
-          for (int e = 0; e < ATT_BN / 2; ++e) pk[e] = pack_bf16(bf16_lo(pk[e]) * alpha, bf16_hi(pk[e]) * alpha);
-          l_tile *= alpha;
-          m_run += (float)kexp;
-        }
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-          for (int c = 0; c < ATT_D / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(lane_addr + TM_O + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-            uint32_t lo[16], hi[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              lo[e] = r[e];
-              hi[e] = r[16 + e];
-            }
-            tmem_st_32x16(lane_addr + TM_O + c * 32, lo);
-            tmem_st_32x16(lane_addr + TM_O + c * 32 + 16, hi);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < ATT_BN / 32; ++c) {
-          uint32_t w16[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) w16[e] = pk[c * 16 + e];
-          tmem_st_32x16(lane_addr + TM_P + c * 16, w16);
-        }
-        tmem_st_wait();
-        l_run = l_run * alpha + l_tile;
       }
       tc_fence_before();
       mbar_arrive(p_full);

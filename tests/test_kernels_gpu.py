@@ -114,6 +114,50 @@ def test_attention_fwd(cuda_lib, B, H, Sq, Sk, causal):
     assert (lse - lref).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_fwd_growing_scores(cuda_lib, causal):
+    """Later key tiles carry scores tens of nats above the first tile's maximum: the single-read softmax must move its
+    reference by exact powers of two (rows renormalise several times) and still match the fp32 softmax and logsumexp;
+    the backward kernels then consume that logsumexp."""
+    from pixparse_b200 import ops
+    torch.manual_seed(9)
+    B, H, Sq, Sk = 2, 2, 256, 448
+    D = H * 64
+    qbuf = torch.randn((B * Sq, D), device=DEV).bfloat16()
+    kv = torch.randn((B, Sk, 2 * D), device=DEV)
+    ramp = torch.linspace(0.05, 40.0, Sk, device=DEV).view(1, Sk, 1)      # key norms grow 800x along the sequence
+    kv[:, :, :D] *= ramp
+    kvbuf = kv.reshape(B * Sk, 2 * D).bfloat16()
+    out, lse = ops.attention_fwd(qbuf, kvbuf, kvbuf, B=B, H=H, Sq=Sq, Sk=Sk, k_col0=0, v_col0=D, causal=causal)
+    q = qbuf.float().view(B, Sq, H, 64).transpose(1, 2)
+    k = kvbuf[:, :D].float().reshape(B, Sk, H, 64).transpose(1, 2)
+    v = kvbuf[:, D:].float().reshape(B, Sk, H, 64).transpose(1, 2)
+    oref, lref = _attn_ref(q, k, v, causal, 0.125)
+    assert (lref.max() - lref.min()).item() > 50          # the case really spans many renormalisations
+    o = out.float().view(B, Sq, H, 64).transpose(1, 2)
+    assert torch.isfinite(o).all() and torch.isfinite(lse).all()
+    assert rel_err(o, oref) < 1e-2
+    assert ((lse - lref).abs() / lref.abs().clamp_min(1.0)).max().item() < 2e-3
+    # backward on the same inputs (both kernels)
+    dout = torch.randn((B * Sq, D), device=DEV).bfloat16()
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    _attn_ref(qr, kr, vr, causal, 0.125)[0].backward(dout.float().view(B, Sq, H, 64).transpose(1, 2))
+    from pixparse_b200 import _lib
+    for query_major in (1, 0):
+        _lib.lib().b200_debug_attention_bwd_query_major(query_major)
+        try:
+            dq = torch.empty((B * Sq, D), device=DEV, dtype=torch.bfloat16)
+            dkv = torch.empty((B * Sk, 2 * D), device=DEV, dtype=torch.bfloat16)
+            ops.attention_bwd(qbuf, kvbuf, kvbuf, out, dout, lse, dq, dkv, dkv, B=B, H=H, Sq=Sq, Sk=Sk, k_col0=0,
+                              v_col0=D, dk_col0=0, dv_col0=D, causal=causal)
+        finally:
+            _lib.lib().b200_debug_attention_bwd_query_major(1)
+        g = lambda t, S: t.float().reshape(B, S, H, 64).transpose(1, 2)
+        assert rel_err(g(dq, Sq), qr.grad) < 3e-2
+        assert rel_err(g(dkv[:, :D], Sk), kr.grad) < 3e-2
+        assert rel_err(g(dkv[:, D:], Sk), vr.grad) < 3e-2
+
+
 @pytest.mark.parametrize("B,H,Sq,Sk,causal", [
     (2, 2, 128, 128, False), (1, 3, 1009, 1009, False), (2, 2, 512, 512, True), (2, 2, 200, 1009, False),
     (1, 2, 4, 300, False), (1, 2, 4, 4, True), (1, 1, 300, 300, True)])
