@@ -33,10 +33,23 @@ def test_gemm_layouts(cuda_lib, a_mn, b_mn, M, N, K, bn):
     assert rel_err(out, ref) < 1e-5      # bf16 products are exact in fp32; only accumulation order differs
 
 
-def test_gemm_epilogues(cuda_lib):
+# (1009, 776, 320): ragged M / N / K inside single tiles; (129, 512, 64) and (300, 256, 128): CTA pairs whose second CTA is
+# (almost) empty; (9000, 1536, 192): 216 pair tiles on 74 pairs -> every CTA loops over several tiles (accumulator-stage
+# phases, aux prefetch and bias restaging across tiles); (100, 768, 256): single-CTA 256-wide tiles (M <= 128)
+@pytest.mark.parametrize("M,N,K", [(1009, 776, 320), (129, 512, 64), (300, 256, 128), (9000, 1536, 192), (100, 768, 256)])
+@pytest.mark.parametrize("single_cta", [0, 1])
+def test_gemm_epilogues(cuda_lib, M, N, K, single_cta):
+    from pixparse_b200 import ops, _lib
+    _lib.lib().b200_debug_gemm_single_cta(single_cta)
+    try:
+        _gemm_epilogues_case(M, N, K)
+    finally:
+        _lib.lib().b200_debug_gemm_single_cta(0)
+
+
+def _gemm_epilogues_case(M, N, K):
     from pixparse_b200 import ops
     torch.manual_seed(2)
-    M, N, K = 1009, 776, 320
     A = torch.randn((M, K), device=DEV).bfloat16()
     B = torch.randn((N, K), device=DEV).bfloat16()
     bias = torch.randn(N, device=DEV)
