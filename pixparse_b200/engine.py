@@ -288,6 +288,11 @@ class CrullerEngine:
         st.final = (x, meanf, rstdf)
         return enc16, (st if save else None)
 
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
+
     def encoder_backward(self, st, d_enc32):
         ar, v = self.arena, self.vit
         a = v.arch
@@ -296,33 +301,84 @@ class CrullerEngine:
         x, meanf, rstdf = st.final
         dx32, dx16 = ops.layernorm_bwd(x, meanf, rstdf, ar.w32("vit.norm.w"), ar.grad("vit.norm.w"),
                                        ar.grad("vit.norm.b"), dy32=d_enc32)
+        # Weight / bias gradients have no consumer before the optimizer, so they can run on a side stream and fill the
+        # partially empty last waves of the main stream's persistent kernels (opt-in: PIXPARSE_B200_SIDE_WGRAD=1).
+        side = self._side_stream() if self.side_wgrad and dx16.is_cuda else None
+        main = torch.cuda.current_stream(dx16.device) if side is not None else None
+
+        def mark():
+            """Event at the current point of the main stream (None without a side stream)."""
+            if side is None:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(main)
+            return ev
+
+        def on_side(fn, keep, after=None):
+            """Enqueue fn() on the side stream behind the main-stream point `after` (default: everything issued so far);
+            returns an event recorded after it. `keep`: tensors the side stream reads (must outlive its kernels)."""
+            if side is None:
+                fn()
+                return None
+            ev = after if after is not None else mark()
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                fn()
+            done = torch.cuda.Event()
+            done.record(side)
+            for t in keep:
+                t.record_stream(side)
+            return done
+
+        def wait(ev):
+            if ev is not None:
+                main.wait_event(ev)
+
         for i in reversed(range(a['depth'])):
             k = f"vit.{i}."
             (x0, mean1, rstd1, ln1, qkv, attn, lse, x1, mean2, rstd2, ln2, hpre, g) = st.blocks[i]
             # --- MLP
+            def w_fc2(dx16=dx16, g=g, k=k):
+                ops.gemm(dx16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"))
+                ops.colsum(dx16, ar.grad(k + "fc2.b"))
+            at_start = mark()           # dx16 of this block is complete here
             d_h = ops.gemm(dx16, ar.w16(k + "fc2.w"), b_mn=True, epi=EPI_DGELU_BF16, aux=hpre)
-            ops.gemm(dx16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"))
-            ops.colsum(dx16, ar.grad(k + "fc2.b"))
+            ev_fc2 = on_side(w_fc2, (dx16, g), after=at_start)      # main-stream kernel first: it is the critical path
+
+            def w_fc1(d_h=d_h, ln2=ln2, k=k):
+                ops.gemm(d_h, ln2, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"))
+                ops.colsum(d_h, ar.grad(k + "fc1.b"))
             d_ln2 = ops.gemm(d_h, ar.w16(k + "fc1.w"), b_mn=True)
-            ops.gemm(d_h, ln2, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"))
-            ops.colsum(d_h, ar.grad(k + "fc1.b"))
+            on_side(w_fc1, (d_h, ln2))
+            wait(ev_fc2)                # the LayerNorm backward below overwrites dx16
             ops.layernorm_bwd(x1, mean2, rstd2, ar.w32(k + "n2.w"), ar.grad(k + "n2.w"), ar.grad(k + "n2.b"),
                               dy16=d_ln2, dres32=dx32, dx32=dx32, dx16=dx16)
             # --- attention
+            def w_proj(dx16=dx16, attn=attn, k=k):
+                ops.gemm(dx16, attn, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "proj.w"))
+                ops.colsum(dx16, ar.grad(k + "proj.b"))
+            at_ln2 = mark()
             d_attn = ops.gemm(dx16, ar.w16(k + "proj.w"), b_mn=True)
-            ops.gemm(dx16, attn, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "proj.w"))
-            ops.colsum(dx16, ar.grad(k + "proj.b"))
+            ev_proj = on_side(w_proj, (dx16, attn), after=at_ln2)
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv, qkv, qkv, attn, d_attn, lse, dqkv, dqkv, dqkv, B=B, H=Hh, Sq=S, Sk=S,
                               q_col0=0, k_col0=D, v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D)
+
+            def w_qkv(dqkv=dqkv, ln1=ln1, k=k):
+                ops.gemm(dqkv, ln1, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "qkv.w"))
+                ops.colsum(dqkv, ar.grad(k + "qkv.b"))
             d_ln1 = ops.gemm(dqkv, ar.w16(k + "qkv.w"), b_mn=True)
-            ops.gemm(dqkv, ln1, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "qkv.w"))
-            ops.colsum(dqkv, ar.grad(k + "qkv.b"))
+            on_side(w_qkv, (dqkv, ln1))
+            wait(ev_proj)               # dx16 is overwritten again
             ops.layernorm_bwd(x0, mean1, rstd1, ar.w32(k + "n1.w"), ar.grad(k + "n1.w"), ar.grad(k + "n1.b"),
                               dy16=d_ln1, dres32=dx32, dx32=dx32, dx16=dx16)
             st.blocks[i] = None
             if self._grad_ready_hook is not None:
+                if side is not None:
+                    main.wait_stream(side)      # the all-reduce of this block's range must see its weight gradients
                 self._grad_ready_hook(k + "n1.w", k + "fc2.b")
+        if side is not None:
+            main.wait_stream(side)
         if a['pre_norm']:
             xp, mean, rstd = st.pre
             ops.layernorm_bwd(xp, mean, rstd, ar.w32("vit.norm_pre.w"), ar.grad("vit.norm_pre.w"),
@@ -522,6 +578,8 @@ class CrullerEngine:
         return d_enc32
 
     _grad_ready_hook = None
+    side_wgrad = bool(int(__import__('os').environ.get('PIXPARSE_B200_SIDE_WGRAD', '0')))   # see encoder_backward
+    _side = None
     on_loss_ready = None        # optional callable(stats): invoked right after the CE kernel is enqueued (async loss read-back)
 
     # ------------------------------------------------------------------------------------------------ public API
