@@ -69,7 +69,20 @@ ce_fwd_bwd_kernel(const bf16* __restrict__ logits, long long ld, const long long
   }
   const uint4* in = reinterpret_cast<const uint4*>(logits + (long long)row * ld);
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
+  // bulk of the row: four independent 16-byte loads in flight per thread (one per iteration left the HBM pipe a third full)
+  const int nbulk = (nvec - 1) / (4 * CE_THREADS) * (4 * CE_THREADS);      // never includes the (possibly padded) last vector
+  for (int i0 = threadIdx.x; i0 < nbulk; i0 += 4 * CE_THREADS) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(in + i0 + u * CE_THREADS);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ce_smem[i0 + u * CE_THREADS] = v[u];
+      mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(bf16_lo(v[u].x), bf16_hi(v[u].x)), fmaxf(bf16_lo(v[u].y), bf16_hi(v[u].y))),
+                           fmaxf(fmaxf(bf16_lo(v[u].z), bf16_hi(v[u].z)), fmaxf(bf16_lo(v[u].w), bf16_hi(v[u].w)))));
+    }
+  }
+  for (int i = nbulk + threadIdx.x; i < nvec; i += CE_THREADS) {
     uint4 v = in[i];
     if (i == nvec - 1 && (V & 7)) {
       // mask the padding columns of the last vector with -inf (bf16 0xff80)
@@ -87,33 +100,37 @@ ce_fwd_bwd_kernel(const bf16* __restrict__ logits, long long ld, const long long
   mx = block_reduce_max(mx, red);   // contains __syncthreads: smem row visible to all
   const float kLog2e = 1.4426950408889634f;
   const float mneg = -mx * kLog2e;
+  const int tvec = (int)(tgt >> 3), te = (int)(tgt & 7);
+  __shared__ float s_xt;
+  // second pass over the staged row: e = exp(x - max) once per element (MUFU work is the larger half of this kernel),
+  // summed in fp32 and written back over the logit as bf16 for the gradient pass; the target logit is rescued first
   float sum = 0.f;
   for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
     const uint4 v = ce_smem[i];
-    sum += exp2f(fmaf(bf16_lo(v.x), kLog2e, mneg)) + exp2f(fmaf(bf16_hi(v.x), kLog2e, mneg)) +
-           exp2f(fmaf(bf16_lo(v.y), kLog2e, mneg)) + exp2f(fmaf(bf16_hi(v.y), kLog2e, mneg)) +
-           exp2f(fmaf(bf16_lo(v.z), kLog2e, mneg)) + exp2f(fmaf(bf16_hi(v.z), kLog2e, mneg)) +
-           exp2f(fmaf(bf16_lo(v.w), kLog2e, mneg)) + exp2f(fmaf(bf16_hi(v.w), kLog2e, mneg));
+    if (i == tvec) s_xt = __bfloat162float(reinterpret_cast<const bf16*>(&v)[te]);
+    const float e0 = ex2_approx(fmaf(bf16_lo(v.x), kLog2e, mneg)), e1 = ex2_approx(fmaf(bf16_hi(v.x), kLog2e, mneg));
+    const float e2 = ex2_approx(fmaf(bf16_lo(v.y), kLog2e, mneg)), e3 = ex2_approx(fmaf(bf16_hi(v.y), kLog2e, mneg));
+    const float e4 = ex2_approx(fmaf(bf16_lo(v.z), kLog2e, mneg)), e5 = ex2_approx(fmaf(bf16_hi(v.z), kLog2e, mneg));
+    const float e6 = ex2_approx(fmaf(bf16_lo(v.w), kLog2e, mneg)), e7 = ex2_approx(fmaf(bf16_hi(v.w), kLog2e, mneg));
+    sum += ((e0 + e1) + (e2 + e3)) + ((e4 + e5) + (e6 + e7));
+    if (out) ce_smem[i] = make_uint4(pack_bf16(e0, e1), pack_bf16(e2, e3), pack_bf16(e4, e5), pack_bf16(e6, e7));
   }
-  sum = block_reduce_sum(sum, red);
+  sum = block_reduce_sum(sum, red);     // contains __syncthreads: s_xt and the rewritten row are visible
   const float n_valid = stats[0];
   const float inv_n = n_valid > 0.f ? 1.0f / n_valid : 0.f;
   if (threadIdx.x == 0) {
-    const float xt = __bfloat162float(reinterpret_cast<const bf16*>(ce_smem)[tgt]);
-    const float l = logf(sum) + mx - xt;
+    const float l = logf(sum) + mx - s_xt;
     if (row_loss) row_loss[row] = l;
     atomicAdd(stats + 1, l * inv_n);
   }
   if (out) {
     const float gs = grad_scale * inv_n;
     const float c = gs / sum;
-    const int tvec = (int)(tgt >> 3), te = (int)(tgt & 7);
+#pragma unroll 4
     for (int i = threadIdx.x; i < nvec; i += CE_THREADS) {
       const uint4 v = ce_smem[i];
-      float p[8] = {exp2f(fmaf(bf16_lo(v.x), kLog2e, mneg)) * c, exp2f(fmaf(bf16_hi(v.x), kLog2e, mneg)) * c,
-                    exp2f(fmaf(bf16_lo(v.y), kLog2e, mneg)) * c, exp2f(fmaf(bf16_hi(v.y), kLog2e, mneg)) * c,
-                    exp2f(fmaf(bf16_lo(v.z), kLog2e, mneg)) * c, exp2f(fmaf(bf16_hi(v.z), kLog2e, mneg)) * c,
-                    exp2f(fmaf(bf16_lo(v.w), kLog2e, mneg)) * c, exp2f(fmaf(bf16_hi(v.w), kLog2e, mneg)) * c};
+      float p[8] = {bf16_lo(v.x) * c, bf16_hi(v.x) * c, bf16_lo(v.y) * c, bf16_hi(v.y) * c,
+                    bf16_lo(v.z) * c, bf16_hi(v.z) * c, bf16_lo(v.w) * c, bf16_hi(v.w) * c};
       if (i == tvec) {
 #pragma unroll
         for (int e = 0; e < 8; ++e)

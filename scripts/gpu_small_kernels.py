@@ -32,3 +32,11 @@ ms = timeit(lambda: ops.layernorm_bwd(x, mean, rstd, g, dg, db, dy16=dy16, dres3
 print(f"layernorm_bwd (dy16 + dres32 -> dx32 + dx16): {ms * 1e3:.1f} us  {(M * D * 16) / ms / 1e6:.0f} GB/s", flush=True)
 ms = timeit(lambda: ops.layernorm_bwd(x, mean, rstd, g, dg, db, dy16=dy16, dx32=dx32, want_bf16=False))
 print(f"layernorm_bwd (dy16 -> dx32): {ms * 1e3:.1f} us  {(M * D * 10) / ms / 1e6:.0f} GB/s", flush=True)
+# cross-entropy at the LM-head shape (16384 rows, V = 50267)
+V, R = 50267, 16384
+ldv = (V + 7) // 8 * 8
+logits = torch.randn((R, ldv), device="cuda").bfloat16()
+tgt = torch.randint(0, V, (R,), device="cuda")
+dl = torch.empty_like(logits)
+ms = timeit(lambda: ops.cross_entropy(logits, tgt, V, dlogits=dl), iters=10)
+print(f"cross_entropy fwd+bwd: {ms * 1e3:.1f} us  {(R * ldv * 4) / ms / 1e6:.0f} GB/s", flush=True)
