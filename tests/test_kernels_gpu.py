@@ -18,7 +18,8 @@ def rel_err(a, b):
 
 # ------------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
-@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (1009, 1000, 200, 256), (515, 776, 1032, 128)])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (1009, 1000, 200, 256), (515, 776, 1032, 128),
+                                      (3, 16, 8, 128), (1, 776, 768, 256), (130, 264, 24, 256)])
 def test_gemm_layouts(cuda_lib, a_mn, b_mn, M, N, K, bn):
     from pixparse_b200 import ops
     torch.manual_seed(1)
