@@ -509,9 +509,17 @@ class CrullerEngine:
         enc16 = st.enc16
         dr = st.drop
         # lm_head (tied to embed_tokens): dgrad + wgrad
-        dy16 = ops.gemm(dlogits, ar.w16("dec.tok"), b_mn=True, K=V)
+        # dgrad of the LM head: K = V = 50 267 makes each of the 192 output tiles 786 k-blocks long, i.e. 2.6 waves of
+        # 0.45 ms on 74 CTA pairs; as a split-K reduce-add into fp32 (which the LayerNorm backward below takes as dy32)
+        # the same work is ~13 even waves and the gradient skips one bf16 rounding
+        if self.lmhead_dgrad_splitk:
+            dy32 = torch.zeros((dlogits.shape[0], D), device=dlogits.device, dtype=torch.float32)
+            ops.gemm(dlogits, ar.w16("dec.tok"), b_mn=True, K=V, epi=EPI_REDUCE_F32, out=dy32)
+            dy16 = None
+        else:
+            dy16 = ops.gemm(dlogits, ar.w16("dec.tok"), b_mn=True, K=V)
+            dy32 = None
         ops.gemm(dlogits, st.h_last16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad("dec.tok"), M=V)
-        dy32 = None
         d_enc32 = None
         for j in reversed(range(nl)):
             k = f"dec.{j}."
@@ -580,6 +588,7 @@ class CrullerEngine:
     _grad_ready_hook = None
     side_wgrad = bool(int(__import__('os').environ.get('PIXPARSE_B200_SIDE_WGRAD', '0')))   # see encoder_backward
     _side = None
+    lmhead_dgrad_splitk = bool(int(__import__('os').environ.get('PIXPARSE_B200_LMHEAD_DGRAD_SPLITK', '1')))
     on_loss_ready = None        # optional callable(stats): invoked right after the CE kernel is enqueued (async loss read-back)
 
     # ------------------------------------------------------------------------------------------------ public API
