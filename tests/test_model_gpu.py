@@ -135,3 +135,24 @@ def test_cruller_base_config1_parity(cuda_lib):
     assert abs(gn.item() - gn_ref.item()) < 1e-2 * gn_ref.item()
     bad = _compare_grads(ours, ref)
     assert not bad, bad[:10]
+
+
+def test_cruller_large_config3_parity(cuda_lib):
+    """BASELINE.json configs[2] architecture: cruller_large (ViT-L/14 pre-norm trunk, D = 1024, 24 blocks, 798x616 pages
+    -> 2509 tokens; bart-large decoder, 10 layers), one page, 64-token target, fp32 reference on device."""
+    from pixparse_b200.engine import engine_for
+    vocab = 50267
+    ref, ours = _build_pair("cruller_large", vocab)
+    image, text, target = _batch("cruller_large", 1, 65)
+    logits_ref, loss_ref = _ref_step(ref, image, text, target, vocab)
+    eng = engine_for(ours)
+    eng.zero_grads()
+    stats = eng.forward_backward(image, text[:, :-1].contiguous(), target[:, 1:].contiguous())
+    torch.cuda.synchronize()
+    assert abs(stats[1].item() - loss_ref.item()) < 1e-3 * abs(loss_ref.item()), (stats[1].item(), loss_ref.item())
+    gn_ref = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in ref.parameters() if p.grad is not None))
+    gn = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in ours.parameters()))
+    assert abs(gn.item() - gn_ref.item()) < 1e-2 * gn_ref.item()
+    bad = _compare_grads(ours, ref)
+    assert not bad, bad[:10]
+
