@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/pixparse_b200.h"
 
@@ -31,6 +32,13 @@ int num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    // PIXPARSE_B200_RESERVE_SMS=<k>: size the persistent grids for k fewer SMs (even, < half the part), e.g. to leave
+    // room for NCCL kernels that otherwise only run in the gaps between kernels owning every SM
+    const char* env = getenv("PIXPARSE_B200_RESERVE_SMS");
+    if (env != nullptr) {
+      int k = atoi(env) & ~1;
+      if (k > 0 && k < n / 2) n -= k;
+    }
     cached = n;
   }
   return cached;
