@@ -51,10 +51,12 @@ def get_next_token(next_token_logits, use_sample: bool = True, temperature: floa
 
 
 def get_generated_tokens(model, tokenizer, encoder_outputs, device_env, max_recursion_length, prompt_token: str,
-                         use_cache: bool = False):
+                         use_cache: bool = False, stop_on_eos: bool = True):
     """use_cache=False is the reference loop (whole prefix re-fed each step). use_cache=True feeds only the last token
     and carries ``past_key_values`` (the branch prepare_inputs_for_inference already has, text_decoder_hf.py:69-70):
-    same token ids, O(steps) instead of O(steps^2) decoder work."""
+    same token ids, O(steps) instead of O(steps^2) decoder work.
+    stop_on_eos=False (benchmarks with random weights) always runs max_recursion_length steps and never reads the
+    "all rows finished" flag back to the host."""
     task_prompt_id = tokenizer.trunk.encode(prompt_token, add_special_tokens=False)[0]
     device = device_env.device
     input_ids = torch.full((encoder_outputs.shape[0], 1), task_prompt_id, dtype=torch.long, device=device)
@@ -70,9 +72,10 @@ def get_generated_tokens(model, tokenizer, encoder_outputs, device_env, max_recu
             past = outputs.past_key_values
         next_token_logits = outputs.logits[:, -1, :]
         next_token_id, _ = get_next_token(next_token_logits, use_sample=False)
-        finished |= next_token_id.squeeze(-1) == eos_token_id
-        if finished.all():
-            break
+        if stop_on_eos:
+            finished |= next_token_id.squeeze(-1) == eos_token_id
+            if finished.all():
+                break
         input_ids = torch.cat([input_ids, next_token_id], dim=-1)
     return input_ids
 

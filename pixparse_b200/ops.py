@@ -231,6 +231,12 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, segments, num_se
          float(beta2), float(eps), int(step), int(zero_grad), stream())
 
 
+def release_workspaces():
+    """Drop the cached attention-backward / grad-norm workspaces (they are sized by the largest call seen)."""
+    _att_ws.clear()
+    _norm_ws.clear()
+
+
 def preprocess_pages(pages_u8, out_size, mean, std, out=None):
     """uint8 grayscale pages [B, Hin, Win] on the device -> normalised fp32 [B, 1, Hout, Wout] (antialiased bicubic)."""
     assert pages_u8.dtype == torch.uint8 and pages_u8.dim() == 3 and pages_u8.is_contiguous()

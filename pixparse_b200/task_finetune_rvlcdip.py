@@ -73,9 +73,7 @@ class TaskCrullerFinetuneRVLCDIP(TaskCrullerPretrain):
         self.image_preprocess_eval = None
         self.train_metrics, self.eval_metrics = {}, {}
         self.max_recursion_length = 1000
-        self.engine = None
-        self.reducer = None
-        self.last_loss = None
+        self._init_step_state()
 
     def train_setup(self, num_batches_per_interval: int):
         if self.state_dict_to_load:
@@ -118,15 +116,16 @@ class TaskCrullerFinetuneRVLCDIP(TaskCrullerPretrain):
 
     def train_step(self, sample: Dict[str, Any]) -> Dict[str, Any]:
         device = self.device_env.device
-        image_input = sample["image"].to(device, non_blocking=True)
-        label = sample["label"].to(device, non_blocking=True).contiguous()
-        text_target = sample["text_target"].to(device, non_blocking=True).contiguous()
+        image_input, label, text_target = self._to_device(sample["image"], sample["label"], sample["text_target"])
+        label, text_target = label.contiguous(), text_target.contiguous()
         result = {}
         accum_steps = self.cfg.opt.grad_accum_steps
         need_update = (self.interval_batch_idx + 1) % accum_steps == 0
         if self.reducer is not None:
             self.reducer.enabled = need_update
             self.reducer.begin()
+        if device.type == 'cuda' and self.engine.on_loss_ready is None:
+            self.engine.on_loss_ready = self._stage_loss_readback
         self.last_loss = self.engine.forward_backward(image_input, label, text_target, grad_scale=1.0 / accum_steps)
         if self.reducer is not None:
             self.reducer.finish()
@@ -135,7 +134,7 @@ class TaskCrullerFinetuneRVLCDIP(TaskCrullerPretrain):
         if self.step % self.eval_frequency == 0 and self.monitor is not None:
             self.monitor.log_step(
                 "finetune", step_idx=self.step, step_end_idx=self.num_intervals * self.num_steps_per_interval,
-                interval=self.interval_idx, loss=self.last_loss[1].item() / accum_steps, lr=self.get_current_lr(),
+                interval=self.interval_idx, loss=self.last_loss_value() / accum_steps, lr=self.get_current_lr(),
                 metrics=None, eval_data=None)
         if not need_update:
             return result

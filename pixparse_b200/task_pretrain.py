@@ -120,13 +120,7 @@ class TaskCrullerPretrain(TaskTrain):
         self.train_metrics = {}
         self.eval_metrics = {}
         self.max_recursion_length = 1000
-        self.engine = None
-        self.reducer = None
-        self.last_loss = None      # device tensor [n_valid, mean_loss] of the latest micro-step
-        self._copy_stream = None   # host batch -> device copies (train_step)
-        self._loss_stream = None   # asynchronous loss read-back (last_loss_value)
-        self._loss_host = None
-        self._loss_event = None
+        self._init_step_state()
 
     # ------------------------------------------------------------------------------------------------------------
     def train_setup(self, num_batches_per_interval: int):
@@ -176,29 +170,40 @@ class TaskCrullerPretrain(TaskTrain):
             self.monitor.log_phase('train', self.interval_idx)
         self.interval_idx += 1
 
-    def train_step(self, sample):
-        image_input, text_input, text_target = sample
-        result = {}
+    def _init_step_state(self):
+        """Per-task state of the host -> device copy and loss read-back machinery (shared with the finetune task)."""
+        self.engine = None
+        self.reducer = None
+        self.last_loss = None      # device tensor [n_valid, mean_loss] of the latest micro-step
+        self._copy_stream = None   # host batch -> device copies (train_step)
+        self._loss_stream = None   # asynchronous loss read-back (last_loss_value)
+        self._loss_host = None
+        self._loss_event = None
+
+    def _to_device(self, *tensors):
+        """Batch tensors -> device. Pinned host tensors are copied on a side stream, so the transfer runs under the tail
+        of the previous step (the host thread is ahead of the GPU) and the compute stream only waits for its event;
+        batches staged ahead by ``data.DevicePrefetcher`` arrive as device tensors and pass through."""
         device = self.device_env.device
-        if image_input.device.type == 'cpu' and image_input.is_pinned() and device.type == 'cuda':
-            # Host batch: copy on a side stream so the transfer runs under the tail of the previous step (the host
-            # thread is ahead of the GPU), then make the compute stream wait for it.
+        if device.type == 'cuda' and all(t.device.type == 'cpu' and t.is_pinned() for t in tensors):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=device)
             main = torch.cuda.current_stream(device)
             with torch.cuda.stream(self._copy_stream):
-                image_input = image_input.to(device, non_blocking=True)
-                text_input = text_input.to(device, non_blocking=True)
-                text_target = text_target.to(device, non_blocking=True)
+                out = [t.to(device, non_blocking=True) for t in tensors]
             main.wait_stream(self._copy_stream)
-            for t in (image_input, text_input, text_target):
+            for t in out:
                 t.record_stream(main)
-            text_input = text_input[:, :-1].contiguous()
-            text_target = text_target[:, 1:].contiguous()
-        else:
-            image_input = image_input.to(device, non_blocking=True)
-            text_input = text_input[:, :-1].to(device, non_blocking=True).contiguous()
-            text_target = text_target[:, 1:].to(device, non_blocking=True).contiguous()
+            return out
+        return [t.to(device, non_blocking=True) for t in tensors]
+
+    def train_step(self, sample):
+        image_input, text_input, text_target = sample
+        result = {}
+        device = self.device_env.device
+        image_input, text_input, text_target = self._to_device(image_input, text_input, text_target)
+        text_input = text_input[:, :-1].contiguous()
+        text_target = text_target[:, 1:].contiguous()
 
         accum_steps = self.cfg.opt.grad_accum_steps
         need_update = (self.interval_batch_idx + 1) % accum_steps == 0
