@@ -8,6 +8,9 @@
  * Contract:
  *   - plain pointers + sizes only; every buffer is owned by the caller (torch caching allocator);
  *     kernels never allocate device memory and keep no global state besides cached function attributes;
+ *   - the large operators take ONE pointer to a POD argument struct whose first field, `struct_size`, must equal
+ *     sizeof(the struct) as this header declares it: a caller built against another layout is rejected (-1) instead of
+ *     being misread. Optional pointers are NULL, optional features are 0. Small helpers keep positional arguments;
  *   - all work is enqueued on the cudaStream_t passed as `stream` (void*), no implicit synchronisation;
  *   - return 0 on success, negative for argument/shape/arch errors, positive = cudaError_t;
  *     b200_last_error() returns a thread-local description; nothing throws across the boundary;
@@ -20,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 /* ---- runtime ---------------------------------------------------------------------------------- */
 const char* b200_last_error(void);
@@ -35,61 +38,187 @@ int b200_device_check(void);
  * Replaces the cuBLASLt calls behind nn.Linear fwd/bwd in timm Attention.qkv/proj, Mlp.fc1/fc2
  * (models/image_encoder_timm.py:13-20), BartAttention q/k/v/out_proj, BartDecoderLayer.fc1/fc2 and lm_head
  * (models/text_decoder_hf.py:13-33), and the patch-embed conv (16x16/16 conv == GEMM over unfolded patches).
+ *
+ * Dropout (BART trains with it live: bart-base dropout = attention_dropout = activation_dropout = 0.1; the reference
+ * never calls model.eval() in train_step) is fused into the RESID / GELU / DGELU epilogues when drop_p > 0.
+ * Masks are stateless: keep(seed, element index) from a counter-based hash, regenerated identically in backward; kept
+ * values are scaled by 1 / (1 - p).
  */
 enum {
   B200_EPI_STORE_BF16 = 0, /* out(bf16)  = acc + bias                                                        */
-  B200_EPI_GELU_BF16  = 1, /* out2(bf16) = h = acc + bias ; out(bf16) = gelu_erf(h)   (timm Mlp / BART fc1)   */
-  B200_EPI_RESID_F32  = 2, /* out(f32)   = aux(f32) + acc + bias   (residual stream; out may alias aux)      */
-  B200_EPI_DGELU_BF16 = 3, /* out(bf16)  = acc * gelu_erf'(aux(bf16))   (fc2 dgrad fused with GELU backward)  */
+  B200_EPI_GELU_BF16  = 1, /* out2(bf16) = h = acc + bias ; out(bf16) = drop(gelu_erf(h))   (timm Mlp / BART fc1) */
+  B200_EPI_RESID_F32  = 2, /* out(f32)   = aux(f32) + drop(acc + bias)   (residual stream; out may alias aux) */
+  B200_EPI_DGELU_BF16 = 3, /* out(bf16)  = mask * acc * gelu_erf'(aux(bf16))   (fc2 dgrad fused with GELU backward) */
   B200_EPI_REDUCE_F32 = 4, /* out(f32)  += acc   via TMA reduce-add, split-K capable (weight gradients)       */
   B200_EPI_STORE_F32  = 5  /* out(f32)   = acc + bias                                                         */
 };
-int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
-                   int M, int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
-                   const float* bias, const void* aux, long long ld_aux, int splits, int block_n, void* stream);
+typedef struct B200GemmArgs {
+  unsigned int struct_size;
+  int epilogue;
+  const void* a;
+  long long lda;
+  int a_mn_major;
+  const void* b;
+  long long ldb;
+  int b_mn_major;
+  int m;
+  int n;
+  int k;
+  void* out;
+  long long ldo;
+  void* out2;
+  long long ldo2;
+  const float* bias;
+  const void* aux;
+  long long ld_aux;
+  /* REDUCE_F32 with A MN-major only (weight gradient dW = dY^T X): bias_grad[m] += sum_k A(m, k), i.e. the column sums
+   * of dY = the nn.Linear bias gradient, accumulated from the A tiles already staged in shared memory (no extra pass
+   * over dY in HBM). NULL = off. */
+  float* bias_grad;
+  int splits;            /* 0 = choose (wave-aware split-K for REDUCE_F32) */
+  int block_n;           /* 0 = choose; 128 or 256 */
+  float drop_p;
+  unsigned int drop_seed;
+} B200GemmArgs;
+int b200_gemm_bf16(const B200GemmArgs* args, void* stream);
 
 /* ---- attention (tcgen05, flash-style, head_dim 64) ---------------------------------------------
- * q/k/v are [B, S, row] bf16 activations with `ld*` elements between tokens; head h occupies columns
- * [*_col0 + 64 h, *_col0 + 64 h + 64). out is [B, Sq, ld_out] (head h at column 64 h); lse is [B, H, Sq] fp32.
+ * q/k/v are [B, S, row] bf16 activations with `ld*` elements between tokens and `*_bstride` elements between batches
+ * (0 = densely packed [B, S, ld]); head h occupies columns [*_col0 + 64 h, *_col0 + 64 h + 64). out is [B, Sq, ld_out]
+ * (head h at column 64 h); lse is [B, H, Sq] fp32 (may be NULL).
  * Replaces F.scaled_dot_product_attention in timm Attention (encoder, non-causal) and BartAttention
- * (decoder causal self-attention and cross-attention; modeling_bart.py:185-258).
+ * (decoder causal self-attention and cross-attention; modeling_bart.py:185-258). Explicit batch strides serve the
+ * KV-cached greedy decode, whose self-attention keys/values live in a pre-allocated [B, T_max, 2D] cache
+ * (models/text_decoder_hf.py:69-70 is the past_key_values branch; utils/ocr_utils.py:165-197 the loop).
+ * key_mask: optional [B, Sk] bytes, 0 = this key is masked for every query of the batch row -- the decoder
+ * attention_mask the reference builds as input_ids.ne(pad) (models/text_decoder_hf.py:68). Inference path only.
+ * drop_p > 0: dropout on the softmax probabilities (normaliser computed before dropping, as F.dropout(softmax)).
  */
-int b200_attention_fwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                       const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
-                       int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream);
-
-/* same with explicit batch strides (elements; 0 = dense [B, S, ld]) -- used by the KV-cached greedy decode, whose
- * self-attention keys/values live in a pre-allocated [B, T_max, 2D] cache (utils/ocr_utils.py:165-197 re-feeds the
- * whole prefix instead; models/text_decoder_hf.py:69-70 is the past_key_values branch this serves) */
-int b200_attention_fwd_strided(const void* q, long long ldq, long long q_bstride, int q_col0, const void* k,
-                               long long ldk, long long k_bstride, int k_col0, const void* v, long long ldv,
-                               long long v_bstride, int v_col0, void* out, long long ld_out, long long out_bstride,
-                               float* lse, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
-                               void* stream);
+typedef struct B200AttentionFwdArgs {
+  unsigned int struct_size;
+  int batch;
+  const void* q;
+  long long ldq;
+  long long q_bstride;
+  int q_col0;
+  int k_col0;
+  const void* k;
+  long long ldk;
+  long long k_bstride;
+  const void* v;
+  long long ldv;
+  long long v_bstride;
+  int v_col0;
+  int heads;
+  void* out;
+  long long ld_out;
+  long long out_bstride;
+  float* lse;
+  const unsigned char* key_mask;
+  long long key_mask_bstride;
+  int sq;
+  int sk;
+  int head_dim;
+  int causal;
+  float scale;
+  float drop_p;
+  unsigned int drop_seed;
+  int reserved;
+} B200AttentionFwdArgs;
+int b200_attention_fwd(const B200AttentionFwdArgs* args, void* stream);
 
 /* backward: dq/dk/dv (bf16, strided like q/k/v) from d_o; `o` and `lse` are the forward outputs.
  * workspace: b200_attention_bwd_workspace_bytes(B, H, Sq) bytes of device memory (fp32 dQ accumulator + row sums). */
 long long b200_attention_bwd_workspace_bytes(int B, int H, int Sq);
-int b200_attention_bwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                       const void* v, long long ldv, int v_col0, const void* o, long long ld_o, const void* d_o,
-                       long long ld_do, int do_col0, const float* lse, void* dq, long long ld_dq, int dq_col0,
-                       void* dk, long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
-                       void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
-                       void* stream);
+typedef struct B200AttentionBwdArgs {
+  unsigned int struct_size;
+  int batch;
+  const void* q;
+  long long ldq;
+  const void* k;
+  long long ldk;
+  const void* v;
+  long long ldv;
+  int q_col0;
+  int k_col0;
+  int v_col0;
+  int do_col0;
+  const void* o;
+  long long ld_o;
+  const void* d_o;
+  long long ld_do;
+  const float* lse;
+  void* dq;
+  long long ld_dq;
+  void* dk;
+  long long ld_dk;
+  void* dv;
+  long long ld_dv;
+  int dq_col0;
+  int dk_col0;
+  int dv_col0;
+  int heads;
+  void* workspace;
+  int sq;
+  int sk;
+  int head_dim;
+  int causal;
+  float scale;
+  float drop_p;
+  unsigned int drop_seed;
+  int reserved;
+} B200AttentionBwdArgs;
+int b200_attention_bwd(const B200AttentionBwdArgs* args, void* stream);
 
 /* ---- LayerNorm (timm Block.norm1/norm2/norm; BART layernorm_embedding / *_layer_norm) --------------
- * fwd: y = (x - mean) * rstd * gamma + beta; x fp32 [rows, dim]; optional bf16 and/or fp32 outputs; mean/rstd saved.
+ * fwd: y = (x - mean) * rstd * gamma + beta; x fp32 [rows, dim]; optional bf16 and/or fp32 outputs; mean/rstd saved;
+ *      drop_p > 0 drops the normalised OUTPUT (dropout(layernorm_embedding(x))).
  * bwd: dy = dy_bf16 + dy_f32 (either may be NULL); dx = LNbwd(dy) + dres_f32 (optional residual-path gradient);
- *      dgamma/dbeta are accumulated (+=).
+ *      dgamma/dbeta are accumulated (+=). in_p/in_seed: the forward's output mask applied to the incoming gradient;
+ *      out_p/out_seed: mask of the sub-layer output feeding this LayerNorm, applied to dx_bf16 only.
  */
-int b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
-                       float* mean, float* rstd, int rows, int dim, float eps, void* stream);
-int b200_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
-                       const float* mean, const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16,
-                       float* dgamma, float* dbeta, int rows, int dim, void* stream);
+typedef struct B200LayerNormFwdArgs {
+  unsigned int struct_size;
+  int rows;
+  const float* x;
+  const float* gamma;
+  const float* beta;
+  void* y_bf16;
+  float* y_f32;
+  float* mean;
+  float* rstd;
+  int dim;
+  float eps;
+  float drop_p;
+  unsigned int drop_seed;
+} B200LayerNormFwdArgs;
+int b200_layernorm_fwd(const B200LayerNormFwdArgs* args, void* stream);
+
+typedef struct B200LayerNormBwdArgs {
+  unsigned int struct_size;
+  int rows;
+  const void* dy_bf16;
+  const float* dy_f32;
+  const float* dres_f32;
+  const float* x;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  float* dx_f32;
+  void* dx_bf16;
+  float* dgamma;
+  float* dbeta;
+  int dim;
+  float in_p;
+  unsigned int in_seed;
+  float out_p;
+  unsigned int out_seed;
+  int reserved;
+} B200LayerNormBwdArgs;
+int b200_layernorm_bwd(const B200LayerNormBwdArgs* args, void* stream);
 
 /* ---- HBM-bound helpers ---------------------------------------------------------------------------- */
-/* out[n] += sum_m dy[m, n]  (bias gradients of every nn.Linear) */
+/* out[n] += sum_m dy[m, n]  (stand-alone column sums; the train step gets its bias gradients from B200GemmArgs.bias_grad) */
 int b200_colsum_bf16(const void* dy, long long ld, int rows, int cols, float* out, void* stream);
 /* timm PatchEmbed: unfold (B, C, H, W) fp32 pixels into [B*gh*gw, C*P*P] bf16 rows for the patch GEMM */
 int b200_patch_unfold(const float* image, void* patches_bf16, int B, int C, int H, int W, int P,
@@ -111,21 +240,45 @@ int b200_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stre
  * nn.CrossEntropyLoss(ignore_index) fwd+bwd in one pass (task_cruller_pretrain.py:118,251-254):
  *   ce_prepare: stats[0] = #valid targets, stats[1] = 0
  *   ce_fwd_bwd: stats[1] += mean loss; dlogits = (softmax - onehot) * grad_scale / #valid (may alias logits)
- * grad_norm: deterministic global L2 norm of the flat gradient arena; out3 = {sumsq, norm, clip coefficient}
- *   (timm dispatch_clip_grad 'norm' -> clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)))
+ * grad_norm: deterministic global L2 norm of the flat gradient arena; out4 = {sumsq, norm, clip coefficient, updates}
+ *   (timm dispatch_clip_grad 'norm' -> clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6)); max_norm <= 0: coef 1).
+ *   out4[3] is a counter the CALLER keeps across steps: it is incremented when the norm is finite, i.e. it counts the
+ *   optimizer updates that were really applied (torch.optim.AdamW's state['step'] under a GradScaler that skips).
  * adamw_step: torch.optim.AdamW semantics over the flat arena, per-tensor lr_scale / weight_decay segments
  *   {int64 end; float lr_scale; float weight_decay}; also refreshes the bf16 shadow weights and zeroes grads.
+ *   With norm_stats (the out4 of grad_norm): gradients are scaled by norm_stats[2], the bias corrections use
+ *   norm_stats[3] as the step number, and a non-finite norm SKIPS the parameter / moment update (what timm's
+ *   NativeScaler / GradScaler.step does, task_cruller_pretrain.py:259-268) while the gradients are still zeroed.
+ *   Without norm_stats: `step` is the 1-based update number and nothing is ever skipped.
  */
 int b200_ce_prepare(const long long* targets, int n, long long ignore_index, float* stats, void* stream);
 int b200_ce_fwd_bwd(const void* logits_bf16, long long ld, const long long* targets, void* dlogits_bf16,
                     long long ldd, float* row_loss, float* stats, int rows, int vocab, long long ignore_index,
                     float grad_scale, void* stream);
-int b200_grad_norm(const float* grads, long long n, float* workspace, float* out3, float max_norm, float pre_scale,
+int b200_grad_norm(const float* grads, long long n, float* workspace, float* out4, float max_norm, float pre_scale,
                    void* stream);
 int b200_grad_norm_workspace_floats(void);
-int b200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16, long long n,
-                    const void* segments, int num_segments, const float* norm_stats, float grad_scale, float lr,
-                    float beta1, float beta2, float eps, int step, int zero_grad, void* stream);
+typedef struct B200AdamWArgs {
+  unsigned int struct_size;
+  int num_segments;
+  float* params;
+  float* grads;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* params_bf16;
+  long long n;
+  const void* segments;
+  const float* norm_stats;
+  float grad_scale;
+  float lr;
+  float beta1;
+  float beta2;
+  float eps;
+  int step;
+  int zero_grad;
+  int reserved;
+} B200AdamWArgs;
+int b200_adamw_step(const B200AdamWArgs* args, void* stream);
 
 /* ---- on-device page preprocessing ------------------------------------------------------
  * uint8 'L' pages [B, Hin, Win] (page_stride bytes apart) -> fp32 [B, 1, Hout, Wout]:
@@ -135,41 +288,6 @@ int b200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_
 long long b200_preprocess_workspace_bytes(int Hout, int Wout);
 int b200_preprocess_pages(const void* pages_u8, int B, int Hin, int Win, long long page_stride, float* out, int Hout,
                           int Wout, float mean, float std_, void* workspace, void* stream);
-
-/* ---- dropout-fused variants ------------------------------------------------------------------------
- * BART trains with dropout live (bart-base: dropout = attention_dropout = activation_dropout = 0.1; the reference
- * never calls model.eval() in train_step). Masks are stateless: keep(seed, element index) from a
- * counter-based hash, regenerated identically in backward; kept values are scaled by 1 / (1 - p).
- *   gemm:      RESID_F32  out = aux + drop(acc + bias)      (BartDecoderLayer: dropout before each residual add)
- *              GELU_BF16  out = drop(gelu(h)), out2 = h      (activation_dropout)
- *              DGELU_BF16 out = mask * acc * gelu'(aux)       (its backward)
- *   layernorm: fwd drops the normalised OUTPUT (dropout(layernorm_embedding(x)));
- *              bwd: in_*  = that output mask applied to the incoming gradient,
- *                   out_* = mask of the sub-layer output feeding this LayerNorm, applied to dx_bf16 only
- *   attention: dropout on the softmax probabilities (normaliser computed before dropping, as F.dropout(softmax))
- */
-int b200_gemm_bf16_dropout(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
-                           int M, int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
-                           const float* bias, const void* aux, long long ld_aux, int splits, int block_n,
-                           float drop_p, unsigned int drop_seed, void* stream);
-int b200_layernorm_fwd_dropout(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
-                               float* mean, float* rstd, int rows, int dim, float eps, float drop_p,
-                               unsigned int drop_seed, void* stream);
-int b200_layernorm_bwd_dropout(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
-                               const float* mean, const float* rstd, const float* gamma, float* dx_f32, void* dx_bf16,
-                               float* dgamma, float* dbeta, int rows, int dim, float in_p, unsigned int in_seed,
-                               float out_p, unsigned int out_seed, void* stream);
-int b200_attention_fwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                               const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
-                               int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
-                               unsigned int drop_seed, void* stream);
-int b200_attention_bwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                               const void* v, long long ldv, int v_col0, const void* o, long long ld_o,
-                               const void* d_o, long long ld_do, int do_col0, const float* lse, void* dq,
-                               long long ld_dq, int dq_col0, void* dk, long long ld_dk, int dk_col0, void* dv,
-                               long long ld_dv, int dv_col0, void* workspace, int B, int H, int Sq, int Sk,
-                               int head_dim, int causal, float scale, float drop_p, unsigned int drop_seed,
-                               void* stream);
 
 /* bring-up aid: override the UMMA shared-memory descriptor fields (-1 keeps the default) */
 int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo, int b_kadv);
