@@ -18,6 +18,7 @@ EPI_RESID_F32 = 2
 EPI_DGELU_BF16 = 3
 EPI_REDUCE_F32 = 4
 EPI_STORE_F32 = 5
+ABI_VERSION = 2      # B200_ABI_VERSION of include/pixparse_b200.h
 
 
 class B200Error(RuntimeError):
@@ -33,7 +34,6 @@ def lib():
                 f"{LIB_PATH} not found: build it with `python -m pixparse_b200.build` "
                 "(there is no CPU / PyTorch fallback for the Cruller hot path)")
         _lib = ctypes.CDLL(LIB_PATH)
-        _lib.b200_last_error.restype = ctypes.c_char_p
         _declare(_lib)
         # A/B switches for bring-up (scripts/gpu_ab.sh): kernel selection only, results are equivalent
         if os.environ.get("PIXPARSE_B200_ATTN_BWD_QUERY_MAJOR"):
@@ -49,20 +49,81 @@ _L = ctypes.c_longlong
 _F = ctypes.c_float
 _U = ctypes.c_uint
 
-# name -> argtypes; must mirror include/pixparse_b200.h exactly (tests/test_abi.py checks the symbol list)
+
+class _Args(ctypes.Structure):
+    """Base of the POD argument structs: field order and C types mirror include/pixparse_b200.h exactly
+    (tests/test_abi.py parses the header and compares); `struct_size` is filled in here and checked by the library."""
+
+    def __init__(self, **kw):
+        super().__init__()
+        names = {f[0] for f in self._fields_}
+        for k, v in kw.items():
+            if k not in names:
+                raise TypeError(f"{type(self).__name__} has no field {k!r}")
+            setattr(self, k, v)
+        self.struct_size = ctypes.sizeof(self)
+
+
+class GemmArgs(_Args):
+    _fields_ = [("struct_size", _U), ("epilogue", _I), ("a", _P), ("lda", _L), ("a_mn_major", _I), ("b", _P), ("ldb", _L),
+                ("b_mn_major", _I), ("m", _I), ("n", _I), ("k", _I), ("out", _P), ("ldo", _L), ("out2", _P), ("ldo2", _L),
+                ("bias", _P), ("aux", _P), ("ld_aux", _L), ("bias_grad", _P), ("splits", _I), ("block_n", _I),
+                ("drop_p", _F), ("drop_seed", _U)]
+
+
+class AttentionFwdArgs(_Args):
+    _fields_ = [("struct_size", _U), ("batch", _I), ("q", _P), ("ldq", _L), ("q_bstride", _L), ("q_col0", _I),
+                ("k_col0", _I), ("k", _P), ("ldk", _L), ("k_bstride", _L), ("v", _P), ("ldv", _L), ("v_bstride", _L),
+                ("v_col0", _I), ("heads", _I), ("out", _P), ("ld_out", _L), ("out_bstride", _L), ("lse", _P),
+                ("key_mask", _P), ("key_mask_bstride", _L), ("sq", _I), ("sk", _I), ("head_dim", _I), ("causal", _I),
+                ("scale", _F), ("drop_p", _F), ("drop_seed", _U), ("reserved", _I)]
+
+
+class AttentionBwdArgs(_Args):
+    _fields_ = [("struct_size", _U), ("batch", _I), ("q", _P), ("ldq", _L), ("k", _P), ("ldk", _L), ("v", _P), ("ldv", _L),
+                ("q_col0", _I), ("k_col0", _I), ("v_col0", _I), ("do_col0", _I), ("o", _P), ("ld_o", _L), ("d_o", _P),
+                ("ld_do", _L), ("lse", _P), ("dq", _P), ("ld_dq", _L), ("dk", _P), ("ld_dk", _L), ("dv", _P),
+                ("ld_dv", _L), ("dq_col0", _I), ("dk_col0", _I), ("dv_col0", _I), ("heads", _I), ("workspace", _P),
+                ("sq", _I), ("sk", _I), ("head_dim", _I), ("causal", _I), ("scale", _F), ("drop_p", _F),
+                ("drop_seed", _U), ("reserved", _I)]
+
+
+class LayerNormFwdArgs(_Args):
+    _fields_ = [("struct_size", _U), ("rows", _I), ("x", _P), ("gamma", _P), ("beta", _P), ("y_bf16", _P), ("y_f32", _P),
+                ("mean", _P), ("rstd", _P), ("dim", _I), ("eps", _F), ("drop_p", _F), ("drop_seed", _U)]
+
+
+class LayerNormBwdArgs(_Args):
+    _fields_ = [("struct_size", _U), ("rows", _I), ("dy_bf16", _P), ("dy_f32", _P), ("dres_f32", _P), ("x", _P),
+                ("mean", _P), ("rstd", _P), ("gamma", _P), ("dx_f32", _P), ("dx_bf16", _P), ("dgamma", _P),
+                ("dbeta", _P), ("dim", _I), ("in_p", _F), ("in_seed", _U), ("out_p", _F), ("out_seed", _U),
+                ("reserved", _I)]
+
+
+class AdamWArgs(_Args):
+    _fields_ = [("struct_size", _U), ("num_segments", _I), ("params", _P), ("grads", _P), ("exp_avg", _P),
+                ("exp_avg_sq", _P), ("params_bf16", _P), ("n", _L), ("segments", _P), ("norm_stats", _P),
+                ("grad_scale", _F), ("lr", _F), ("beta1", _F), ("beta2", _F), ("eps", _F), ("step", _I),
+                ("zero_grad", _I), ("reserved", _I)]
+
+
+# C struct name (header) -> ctypes mirror
+STRUCTS = {"B200GemmArgs": GemmArgs, "B200AttentionFwdArgs": AttentionFwdArgs, "B200AttentionBwdArgs": AttentionBwdArgs,
+           "B200LayerNormFwdArgs": LayerNormFwdArgs, "B200LayerNormBwdArgs": LayerNormBwdArgs, "B200AdamWArgs": AdamWArgs}
+
+# name -> argtypes; mirrors include/pixparse_b200.h (tests/test_abi.py compares every prototype and struct field)
 SIGNATURES = {
     "b200_abi_version": [],
     "b200_device_check": [],
     "b200_debug_gemm_desc": [_I, _I, _I, _I, _I, _I],
     "b200_debug_gemm_single_cta": [_I],
     "b200_debug_attention_bwd_query_major": [_I],
-    "b200_attention_fwd": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _P],
-    "b200_attention_fwd_strided": [_P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _P, _I, _I, _I, _I, _I, _I,
-                                   _F, _P],
-    "b200_attention_bwd": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _L, _I, _P, _P, _L, _I, _P, _L, _I, _P, _L,
-                           _I, _P, _I, _I, _I, _I, _I, _I, _F, _P],
-    "b200_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
-    "b200_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "b200_gemm_bf16": [ctypes.POINTER(GemmArgs), _P],
+    "b200_attention_fwd": [ctypes.POINTER(AttentionFwdArgs), _P],
+    "b200_attention_bwd": [ctypes.POINTER(AttentionBwdArgs), _P],
+    "b200_layernorm_fwd": [ctypes.POINTER(LayerNormFwdArgs), _P],
+    "b200_layernorm_bwd": [ctypes.POINTER(LayerNormBwdArgs), _P],
+    "b200_adamw_step": [ctypes.POINTER(AdamWArgs), _P],
     "b200_colsum_bf16": [_P, _L, _I, _I, _P, _P],
     "b200_patch_unfold": [_P, _P, _I, _I, _I, _I, _I, _L, _P],
     "b200_tokens_assemble": [_P, _P, _P, _P, _I, _I, _I, _P],
@@ -74,16 +135,13 @@ SIGNATURES = {
     "b200_ce_fwd_bwd": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _L, _F, _P],
     "b200_grad_norm": [_P, _L, _P, _P, _F, _F, _P],
     "b200_grad_norm_workspace_floats": [],
-    "b200_adamw_step": [_P, _P, _P, _P, _P, _L, _P, _I, _P, _F, _F, _F, _F, _F, _I, _I, _P],
     "b200_preprocess_pages": [_P, _I, _I, _I, _L, _P, _I, _I, _F, _F, _P, _P],
-    "b200_gemm_bf16_dropout": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _F, _U, _P],
-    "b200_layernorm_fwd_dropout": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _U, _P],
-    "b200_layernorm_bwd_dropout": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _U, _F, _U, _P],
-    "b200_attention_fwd_dropout": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _F, _U, _P],
-    "b200_attention_bwd_dropout": [_P, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _P, _L, _I, _P, _P, _L, _I, _P, _L, _I, _P,
-                                   _L, _I, _P, _I, _I, _I, _I, _I, _I, _F, _F, _U, _P],
-    "b200_gemm_bf16": [_P, _L, _I, _P, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _P, _L, _I, _I, _P],
 }
+# entry points whose return type is not int
+RESTYPES = {"b200_last_error": ctypes.c_char_p, "b200_attention_bwd_workspace_bytes": ctypes.c_longlong,
+            "b200_preprocess_workspace_bytes": ctypes.c_longlong}
+OTHER_SIGNATURES = {"b200_last_error": [], "b200_attention_bwd_workspace_bytes": [_I, _I, _I],
+                    "b200_preprocess_workspace_bytes": [_I, _I]}
 
 
 def _declare(l):
@@ -91,10 +149,14 @@ def _declare(l):
         fn = getattr(l, name)
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
-    l.b200_attention_bwd_workspace_bytes.argtypes = [_I, _I, _I]
-    l.b200_attention_bwd_workspace_bytes.restype = ctypes.c_longlong
-    l.b200_preprocess_workspace_bytes.argtypes = [_I, _I]
-    l.b200_preprocess_workspace_bytes.restype = ctypes.c_longlong
+    for name, argtypes in OTHER_SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = RESTYPES[name]
+    got = l.b200_abi_version()
+    if got != ABI_VERSION:
+        raise B200Error(f"{LIB_PATH} implements C-ABI version {got}, this package binds version {ABI_VERSION}: rebuild it "
+                        "with `python -m pixparse_b200.build`")
 
 
 def check(rc, what):
@@ -115,7 +177,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (grad_norm: partial + final; attention_bwd: prep + main + dq convert)
-_KERNELS_PER_CALL = {"b200_grad_norm": 2, "b200_attention_bwd": 3, "b200_attention_bwd_dropout": 3}
+_KERNELS_PER_CALL = {"b200_grad_norm": 2, "b200_attention_bwd": 3}
 _launches = 0
 _profile = None     # {name: [(start_event, end_event, flops), ...]} while profile_ops() is active
 
@@ -132,16 +194,24 @@ def launch_count():
 def call(name, *args):
     global _launches
     prof = _profile
-    pname = name[:-8] if name.endswith("_dropout") else name      # dropout variants are profiled with their base op
+    pname = name
     if prof is not None and pname in prof:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib(), name)(*args)
         e1.record()
-        is_gemm = name.startswith("b200_gemm_bf16")
-        flops = 2.0 * args[6] * args[7] * args[8] if is_gemm else 0.0
-        tag = (f"gemm a_mn={args[2]} b_mn={args[5]} epi={args[9]}" if is_gemm else name)
+        flops, tag = 0.0, name
+        a0 = args[0] if args else None
+        if isinstance(a0, GemmArgs):
+            flops = 2.0 * a0.m * a0.n * a0.k
+            tag = f"gemm a_mn={a0.a_mn_major} b_mn={a0.b_mn_major} epi={a0.epilogue}"
+        elif isinstance(a0, AttentionFwdArgs):      # full Sq x Sk (bench.py / BASELINE.md convention), head_dim 64
+            flops = 4.0 * a0.batch * a0.heads * a0.sq * a0.sk * 64
+            tag = f"attention_fwd Sq={a0.sq} Sk={a0.sk} causal={a0.causal} drop={int(a0.drop_p > 0)}"
+        elif isinstance(a0, AttentionBwdArgs):
+            flops = 10.0 * a0.batch * a0.heads * a0.sq * a0.sk * 64
+            tag = f"attention_bwd Sq={a0.sq} Sk={a0.sk} causal={a0.causal} drop={int(a0.drop_p > 0)}"
         prof[pname].append((e0, e1, flops, tag))
     else:
         rc = getattr(lib(), name)(*args)

@@ -506,42 +506,18 @@ extern "C" long long b200_attention_bwd_workspace_bytes(int B, int H, int Sq) {
   return (head + 2 * (long long)B * H * sq_pad) * 4;
 }
 
-static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                              const void* v, long long ldv, int v_col0, const void* o, long long ld_o, const void* d_o,
-                              long long ld_do, int do_col0, const float* lse, void* dq, long long ld_dq, int dq_col0,
-                              void* dk, long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
-                              void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
-                              float drop_p, unsigned int drop_seed, void* stream);
-
-extern "C" int b200_attention_bwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                                  const void* v, long long ldv, int v_col0, const void* o, long long ld_o,
-                                  const void* d_o, long long ld_do, int do_col0, const float* lse, void* dq,
-                                  long long ld_dq, int dq_col0, void* dk, long long ld_dk, int dk_col0, void* dv,
-                                  long long ld_dv, int dv_col0, void* workspace, int B, int H, int Sq, int Sk,
-                                  int head_dim, int causal, float scale, void* stream) {
-  return attention_bwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, o, ld_o, d_o, ld_do, do_col0, lse, dq, ld_dq,
-                            dq_col0, dk, ld_dk, dk_col0, dv, ld_dv, dv_col0, workspace, B, H, Sq, Sk, head_dim, causal,
-                            scale, 0.f, 0u, stream);
-}
-
-extern "C" int b200_attention_bwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk,
-                                          int k_col0, const void* v, long long ldv, int v_col0, const void* o,
-                                          long long ld_o, const void* d_o, long long ld_do, int do_col0,
-                                          const float* lse, void* dq, long long ld_dq, int dq_col0, void* dk,
-                                          long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
-                                          void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal,
-                                          float scale, float drop_p, unsigned int drop_seed, void* stream) {
-  return attention_bwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, o, ld_o, d_o, ld_do, do_col0, lse, dq, ld_dq,
-                            dq_col0, dk, ld_dk, dk_col0, dv, ld_dv, dv_col0, workspace, B, H, Sq, Sk, head_dim, causal,
-                            scale, drop_p, drop_seed, stream);
-}
-
-static int attention_bwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                              const void* v, long long ldv, int v_col0, const void* o, long long ld_o, const void* d_o,
-                              long long ld_do, int do_col0, const float* lse, void* dq, long long ld_dq, int dq_col0,
-                              void* dk, long long ld_dk, int dk_col0, void* dv, long long ld_dv, int dv_col0,
-                              void* workspace, int B, int H, int Sq, int Sk, int head_dim, int causal, float scale,
-                              float drop_p, unsigned int drop_seed, void* stream) {
+extern "C" int b200_attention_bwd(const B200AttentionBwdArgs* a, void* stream) {
+  B200_CHECK_STRUCT(a, B200AttentionBwdArgs, "b200_attention_bwd");
+  const void *q = a->q, *k = a->k, *v = a->v, *o = a->o, *d_o = a->d_o;
+  const long long ldq = a->ldq, ldk = a->ldk, ldv = a->ldv, ld_o = a->ld_o, ld_do = a->ld_do;
+  const long long ld_dq = a->ld_dq, ld_dk = a->ld_dk, ld_dv = a->ld_dv;
+  const int q_col0 = a->q_col0, k_col0 = a->k_col0, v_col0 = a->v_col0, do_col0 = a->do_col0;
+  const int dq_col0 = a->dq_col0, dk_col0 = a->dk_col0, dv_col0 = a->dv_col0;
+  const float* lse = a->lse;
+  void *dq = a->dq, *dk = a->dk, *dv = a->dv, *workspace = a->workspace;
+  const int B = a->batch, H = a->heads, Sq = a->sq, Sk = a->sk, head_dim = a->head_dim, causal = a->causal;
+  const float scale = a->scale, drop_p = a->drop_p;
+  const unsigned int drop_seed = a->drop_seed;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(head_dim == AB_D, "b200_attention_bwd: head_dim %d unsupported (only 64)", head_dim);
   B200_CHECK_ARG(q && k && v && o && d_o && lse && dq && dk && dv && workspace, "b200_attention_bwd: null argument");

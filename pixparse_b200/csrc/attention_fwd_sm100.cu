@@ -44,9 +44,12 @@ struct AttFwdParams {
   float* lse;              // [B, H, Sq] natural-log logsumexp of the scaled scores
   int q_col0, k_col0, v_col0;   // column offsets of head 0 inside the Q / K / V row
   uint32_t drop_threshold16, drop_seed;   // attention-probability dropout (BART attention_dropout); 0 = off
+  const uint8_t* key_mask;                // [B, Sk] bytes (key_mask_bstride apart), 0 = key hidden from every query; KMASK kernels only
+  long long key_mask_bstride;
 };
 
-template <bool DROP>
+// KMASK: key-padding mask (decoder attention_mask = input_ids.ne(pad), text_decoder_hf.py:68); inference path, no dropout
+template <bool DROP, bool KMASK>
 __global__ void __launch_bounds__(ATT_THREADS, DROP ? 4 : 3)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
@@ -173,9 +176,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     float l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const int k0 = j * ATT_BN;
-      const bool need_mask = (k0 + ATT_BN > p.Sk) || (p.causal && (k0 + ATT_BN - 1 > q0 + causal_shift));
+      const bool need_mask = KMASK || (k0 + ATT_BN > p.Sk) || (p.causal && (k0 + ATT_BN - 1 > q0 + causal_shift));
       int kmax = p.Sk - 1;                                   // largest visible key index for this row
       if (p.causal) kmax = min(kmax, qidx + causal_shift);
+      uint64_t kbits = ~0ull;                                // bit i: key k0 + i is not padding
+      if (KMASK) {
+        const uint8_t* mrow = p.key_mask + (long long)b * p.key_mask_bstride + k0;
+        kbits = 0ull;
+#pragma unroll 8
+        for (int i = 0; i < ATT_BN; ++i)
+          if (k0 + i < p.Sk && mrow[i] != 0) kbits |= 1ull << i;
+      }
+      auto vis = [&](int i) { return (k0 + i <= kmax) && (!KMASK || ((kbits >> i) & 1ull) != 0ull); };
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       // Tensor-memory reads bound this kernel (two 32 KB passes over S per tile = ~1000 cycles at the measured ~64 B/clk
@@ -200,8 +212,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_run));
               float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_run));
               if (MASKED) {
-                if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
-                if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
+                if (!vis(c * 32 + 2 * e)) p0 = 0.f;
+                if (!vis(c * 32 + 2 * e + 1)) p1 = 0.f;
               }
               pmax = fmaxf(pmax, fmaxf(p0, p1));
               l_tile += p0 + p1;        // the softmax normaliser uses the un-dropped probabilities
@@ -271,7 +283,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (need_mask) {
   #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (k0 + c * 32 + e <= kmax) mx = fmaxf(mx, __uint_as_float(r[e]));
+              if (vis(c * 32 + e)) mx = fmaxf(mx, __uint_as_float(r[e]));
           } else {
   #pragma unroll
             for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
@@ -319,8 +331,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
               float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * e]), p.scale_log2, -m_use));
               float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * e + 1]), p.scale_log2, -m_use));
               if (MASKED) {
-                if (k0 + c * 32 + 2 * e > kmax) p0 = 0.f;
-                if (k0 + c * 32 + 2 * e + 1 > kmax) p1 = 0.f;
+                if (!vis(c * 32 + 2 * e)) p0 = 0.f;
+                if (!vis(c * 32 + 2 * e + 1)) p1 = 0.f;
               }
               l_tile += p0 + p1;        // the softmax normaliser uses the un-dropped probabilities
               if (DROP)
@@ -387,77 +399,51 @@ int make_att_tmap(CUtensorMap* m, const void* base, int B, int S, long long widt
 
 using namespace b200;
 
-static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                              const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse, int B,
-                              int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
-                              unsigned int drop_seed, void* stream, long long q_bs = 0, long long k_bs = 0,
-                              long long v_bs = 0, long long out_bs = 0);
-
-extern "C" int b200_attention_fwd(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                                  const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse,
-                                  int B, int H, int Sq, int Sk, int head_dim, int causal, float scale, void* stream) {
-  return attention_fwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ld_out, lse, B, H, Sq, Sk, head_dim,
-                            causal, scale, 0.f, 0u, stream);
-}
-
-extern "C" int b200_attention_fwd_dropout(const void* q, long long ldq, int q_col0, const void* k, long long ldk,
-                                          int k_col0, const void* v, long long ldv, int v_col0, void* out,
-                                          long long ld_out, float* lse, int B, int H, int Sq, int Sk, int head_dim,
-                                          int causal, float scale, float drop_p, unsigned int drop_seed,
-                                          void* stream) {
-  return attention_fwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ld_out, lse, B, H, Sq, Sk, head_dim,
-                            causal, scale, drop_p, drop_seed, stream);
-}
-
-// KV-cache friendly variant: explicit batch strides (elements) for q / k / v / out; 0 = densely packed [B, S, ld]
-extern "C" int b200_attention_fwd_strided(const void* q, long long ldq, long long q_bstride, int q_col0, const void* k,
-                                          long long ldk, long long k_bstride, int k_col0, const void* v, long long ldv,
-                                          long long v_bstride, int v_col0, void* out, long long ld_out,
-                                          long long out_bstride, float* lse, int B, int H, int Sq, int Sk, int head_dim,
-                                          int causal, float scale, void* stream) {
-  return attention_fwd_impl(q, ldq, q_col0, k, ldk, k_col0, v, ldv, v_col0, out, ld_out, lse, B, H, Sq, Sk, head_dim,
-                            causal, scale, 0.f, 0u, stream, q_bstride, k_bstride, v_bstride, out_bstride);
-}
-
-static int attention_fwd_impl(const void* q, long long ldq, int q_col0, const void* k, long long ldk, int k_col0,
-                              const void* v, long long ldv, int v_col0, void* out, long long ld_out, float* lse, int B,
-                              int H, int Sq, int Sk, int head_dim, int causal, float scale, float drop_p,
-                              unsigned int drop_seed, void* stream, long long q_bs, long long k_bs, long long v_bs,
-                              long long out_bs) {
+extern "C" int b200_attention_fwd(const B200AttentionFwdArgs* a, void* stream) {
+  B200_CHECK_STRUCT(a, B200AttentionFwdArgs, "b200_attention_fwd");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  B200_CHECK_ARG(head_dim == ATT_D, "b200_attention_fwd: head_dim %d unsupported (only 64)", head_dim);
-  B200_CHECK_ARG(q && k && v && out && B > 0 && H > 0 && Sq > 0 && Sk > 0, "b200_attention_fwd: bad arguments");
-  B200_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ld_out % 8 == 0,
+  const int B = a->batch, H = a->heads, Sq = a->sq, Sk = a->sk;
+  B200_CHECK_ARG(a->head_dim == ATT_D, "b200_attention_fwd: head_dim %d unsupported (only 64)", a->head_dim);
+  B200_CHECK_ARG(a->q && a->k && a->v && a->out && B > 0 && H > 0 && Sq > 0 && Sk > 0, "b200_attention_fwd: bad arguments");
+  B200_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ld_out % 8 == 0,
                  "b200_attention_fwd: row strides must be multiples of 8 elements");
-  B200_CHECK_ARG(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "b200_attention_fwd: column offsets % 8");
-  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "b200_attention_fwd: out must be 16-byte aligned");
-  if (causal) B200_CHECK_ARG(Sk >= Sq, "b200_attention_fwd: causal attention needs Sk >= Sq");
+  B200_CHECK_ARG(a->q_col0 % 8 == 0 && a->k_col0 % 8 == 0 && a->v_col0 % 8 == 0, "b200_attention_fwd: column offsets % 8");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "b200_attention_fwd: out must be 16-byte aligned");
+  B200_CHECK_ARG(a->q_bstride % 8 == 0 && a->k_bstride % 8 == 0 && a->v_bstride % 8 == 0 && a->out_bstride % 8 == 0,
+                 "b200_attention_fwd: batch strides must be multiples of 8 elements");
+  if (a->causal) B200_CHECK_ARG(Sk >= Sq, "b200_attention_fwd: causal attention needs Sk >= Sq");
+  B200_CHECK_ARG(a->drop_p >= 0.f && a->drop_p < 1.f, "b200_attention_fwd: dropout p must be in [0, 1)");
+  B200_CHECK_ARG(!(a->key_mask != nullptr && a->drop_p > 0.f),
+                 "b200_attention_fwd: key_mask is an inference-path feature (no dropout variant)");
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_att_tmap(&tq, q, B, Sq, q_col0 + (long long)H * ATT_D, ldq, ATT_BM, q_bs))) return rc;
-  if ((rc = make_att_tmap(&tk, k, B, Sk, k_col0 + (long long)H * ATT_D, ldk, ATT_BN, k_bs))) return rc;
-  if ((rc = make_att_tmap(&tv, v, B, Sk, v_col0 + (long long)H * ATT_D, ldv, ATT_BN, v_bs))) return rc;
+  if ((rc = make_att_tmap(&tq, a->q, B, Sq, a->q_col0 + (long long)H * ATT_D, a->ldq, ATT_BM, a->q_bstride))) return rc;
+  if ((rc = make_att_tmap(&tk, a->k, B, Sk, a->k_col0 + (long long)H * ATT_D, a->ldk, ATT_BN, a->k_bstride))) return rc;
+  if ((rc = make_att_tmap(&tv, a->v, B, Sk, a->v_col0 + (long long)H * ATT_D, a->ldv, ATT_BN, a->v_bstride))) return rc;
   AttFwdParams p;
-  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = causal;
-  p.scale_log2 = scale * 1.4426950408889634f;
-  p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out; p.lse = lse;
-  p.out_bstride = out_bs > 0 ? out_bs : (long long)Sq * ld_out;
-  B200_CHECK_ARG(q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && out_bs % 8 == 0, "b200_attention_fwd: batch strides must be multiples of 8 elements");
-  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
-  B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "b200_attention_fwd: dropout p must be in [0, 1)");
-  p.drop_threshold16 = drop_p > 0.f ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
-  p.drop_seed = drop_seed;
+  p.B = B; p.H = H; p.Sq = Sq; p.Sk = Sk; p.causal = a->causal;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(a->out); p.ld_out = a->ld_out; p.lse = a->lse;
+  p.out_bstride = a->out_bstride > 0 ? a->out_bstride : (long long)Sq * a->ld_out;
+  p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
+  p.drop_threshold16 = a->drop_p > 0.f ? (uint32_t)(a->drop_p * 65536.0f + 0.5f) : 0u;
+  p.drop_seed = a->drop_seed;
+  p.key_mask = a->key_mask;
+  p.key_mask_bstride = a->key_mask_bstride > 0 ? a->key_mask_bstride : (long long)Sk;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+      e = cudaFuncSetAttribute(attention_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(attention_fwd)");
     configured = true;
   }
   dim3 grid((Sq + ATT_BM - 1) / ATT_BM, H, B);
-  if (p.drop_threshold16 != 0u) attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
-  else attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
+  if (p.drop_threshold16 != 0u) attention_fwd_kernel<true, false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
+  else if (p.key_mask != nullptr) attention_fwd_kernel<false, true><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
+  else attention_fwd_kernel<false, false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
   B200_CHECK_LAUNCH("attention_fwd");
   return 0;
 }

@@ -29,6 +29,14 @@ int check_cuda(cudaError_t e, const char* what);
     }                                        \
   } while (0)
 
+// argument structs of the C-ABI start with their own size: a caller built against another layout is rejected
+#define B200_CHECK_STRUCT(args, T, name)                                                                      \
+  do {                                                                                                       \
+    B200_CHECK_ARG((args) != nullptr, name ": null argument struct");                                        \
+    B200_CHECK_ARG((args)->struct_size == sizeof(T), name ": struct_size %u != %zu (caller built against a "  \
+                   "different include/pixparse_b200.h)", (args)->struct_size, sizeof(T));                   \
+  } while (0)
+
 #define B200_CHECK_LAUNCH(name)                                   \
   do {                                                            \
     cudaError_t e__ = cudaGetLastError();                         \
@@ -402,6 +410,11 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // take the 32-bit shared address (smem_u32) instead.
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;

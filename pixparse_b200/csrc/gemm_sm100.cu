@@ -44,6 +44,9 @@ struct GemmParams {
   uint32_t drop_threshold16, drop_seed;
   // STORE_BF16 / GELU_BF16: outputs leave through TMA stores (needs 16-byte aligned base and row pitch)
   int tma_epi;
+  // REDUCE_F32 + A MN-major (weight gradients): bias_grad[m] += sum_k A(m, k), summed from the staged A tiles by the two
+  // otherwise idle control warps (10, 11) on the n_tile == 0 work items
+  float* bias_grad;
 };
 
 // debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
@@ -254,7 +257,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
   uint64_t* aux_full_bar = tmem_empty_bar + 2;  // [group][slot]: aux tile landed (TMA transaction bytes)
   uint64_t* aux_free_bar = aux_full_bar + 4;    // [group][slot]: all 128 threads of the group have read the aux tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_free_bar + 4);
+  uint64_t* landed_bar = aux_free_bar + 4;      // [STAGES] CTA pairs + bias_grad: "stage landed", relayed by the leader to its peer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(landed_bar + STAGES);
+  static_assert((2 * STAGES + 12 + STAGES) * 8 + 4 <= 256, "barrier block overflows its 256 bytes");
+  constexpr bool CAN_BIASG = (EPI == B200_EPI_REDUCE_F32) && A_MN;
+  const bool biasg = CAN_BIASG && p.bias_grad != nullptr;
   float* epi_bias = reinterpret_cast<float*>(epi_buf + 2 * Cfg::EPI_GROUP_BYTES + 256);   // 2 groups x 128 floats
 
   const int warp = threadIdx.x >> 5;
@@ -273,7 +280,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 11 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], biasg ? 3 : 1);     // MMA commit (+ the two bias-gradient warps)
+      mbar_init(&landed_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -419,6 +427,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           acc = 0;
           acc_phase ^= 1;
         }
+      }
+    }
+  } else if (warp >= 10 && biasg) {
+    // ===================== bias-gradient warps =====================
+    // dW = dY^T X reduces over tokens; its A operand IS dY (MN-major: 64 tokens x 128 features per stage, two 64-feature
+    // chunks of 128-byte rows, SWIZZLE_128B), so the nn.Linear bias gradient colsum(dY) is summed straight from the staged
+    // tiles: warp 10 / 11 take one chunk each, lane l owns features 2l, 2l+1 (one conflict-free 128-byte row read per
+    // token). Only the n_tile == 0 work items contribute (every n_tile sees the same A). Every stage is waited for and
+    // released by these warps too, which keeps them in lock-step with the ring (an arrive can never run a phase ahead).
+    const int chunk = warp - 10;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = worker; w < total_work; w += n_workers) {
+      int m_tile, n_tile, split;
+      decode_work(p, w, m_tile, n_tile, split);
+      if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
+      const bool mine = (n_tile == 0);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      f32x2 acc0 = f2_splat(0.f), acc1 = f2_splat(0.f);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (CG == 2 && cta_rank != 0) {
+          mbar_wait(&landed_bar[stage], phase);
+        } else {
+          mbar_wait(&full_bar[stage], phase);
+          // all bytes of a pair's stage are credited to the leader's barrier: relay "landed" to the peer CTA
+          if (CG == 2 && chunk == 0 && lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&landed_bar[stage]), 1));
+        }
+        if (mine) {
+          const uint32_t base = smem_u32(smem + stage * Cfg::STAGE_BYTES) + chunk * (BK * 128) + (lane & 3) * 4;
+          const int c16 = lane >> 2;
+#pragma unroll 8
+          for (int r = 0; r < BK; r += 2) {
+            const uint32_t w0 = lds32(base + r * 128 + ((c16 ^ (r & 7)) << 4));
+            const uint32_t w1 = lds32(base + (r + 1) * 128 + ((c16 ^ ((r + 1) & 7)) << 4));
+            acc0 = f2_add(acc0, f2_pack(bf16_lo(w0), bf16_hi(w0)));
+            acc1 = f2_add(acc1, f2_pack(bf16_lo(w1), bf16_hi(w1)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (mine) {
+        float s0, s1;
+        f2_unpack(f2_add(acc0, acc1), s0, s1);
+        const int row = m_tile * BM + chunk * 64 + 2 * lane;
+        if (row < p.M) atomicAdd(p.bias_grad + row, s0);
+        if (row + 1 < p.M) atomicAdd(p.bias_grad + row + 1, s1);
       }
     }
   } else if (warp < 8) {
@@ -770,32 +830,16 @@ extern "C" int b200_debug_gemm_single_cta(int on) {
   return 0;
 }
 
-static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
-                     int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
-                     const float* bias, const void* aux, long long ld_aux, int splits, int block_n, float drop_p,
-                     unsigned int drop_seed, void* stream_);
-
-extern "C" int b200_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
-                              int b_mn_major, int M, int N, int K, int epilogue, void* out, long long ldo,
-                              void* out2, long long ldo2, const float* bias, const void* aux, long long ld_aux,
-                              int splits, int block_n, void* stream_) {
-  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, out, ldo, out2, ldo2, bias, aux, ld_aux,
-                   splits, block_n, 0.f, 0u, stream_);
-}
-
-extern "C" int b200_gemm_bf16_dropout(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
-                                      int b_mn_major, int M, int N, int K, int epilogue, void* out, long long ldo,
-                                      void* out2, long long ldo2, const float* bias, const void* aux,
-                                      long long ld_aux, int splits, int block_n, float drop_p,
-                                      unsigned int drop_seed, void* stream_) {
-  return gemm_impl(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epilogue, out, ldo, out2, ldo2, bias, aux, ld_aux,
-                   splits, block_n, drop_p, drop_seed, stream_);
-}
-
-static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major, int M,
-                     int N, int K, int epilogue, void* out, long long ldo, void* out2, long long ldo2,
-                     const float* bias, const void* aux, long long ld_aux, int splits, int block_n, float drop_p,
-                     unsigned int drop_seed, void* stream_) {
+extern "C" int b200_gemm_bf16(const B200GemmArgs* args, void* stream_) {
+  B200_CHECK_STRUCT(args, B200GemmArgs, "b200_gemm_bf16");
+  const void* A = args->a; const long long lda = args->lda; const int a_mn_major = args->a_mn_major;
+  const void* B = args->b; const long long ldb = args->ldb; const int b_mn_major = args->b_mn_major;
+  const int M = args->m, N = args->n, K = args->k, epilogue = args->epilogue;
+  void* out = args->out; const long long ldo = args->ldo; void* out2 = args->out2; const long long ldo2 = args->ldo2;
+  const float* bias = args->bias; const void* aux = args->aux; const long long ld_aux = args->ld_aux;
+  int splits = args->splits; const int block_n = args->block_n;
+  const float drop_p = args->drop_p; const unsigned int drop_seed = args->drop_seed;
+  float* bias_grad = args->bias_grad;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "b200_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   B200_CHECK_ARG(A && B && out, "b200_gemm_bf16: null operand");
@@ -857,6 +901,10 @@ static int gemm_impl(const void* A, long long lda, int a_mn_major, const void* B
   p.group_m = 8;
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
   p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
+  p.bias_grad = bias_grad;
+  if (bias_grad != nullptr)
+    B200_CHECK_ARG(epilogue == B200_EPI_REDUCE_F32 && a_mn_major,
+                   "b200_gemm_bf16: bias_grad is fused only into weight gradients (REDUCE_F32 epilogue, A MN-major)");
   p.drop_threshold16 = 0; p.drop_seed = drop_seed;
   if (drop_p > 0.f) {
     B200_CHECK_ARG(drop_p < 1.f, "b200_gemm_bf16_dropout: p must be in [0, 1)");

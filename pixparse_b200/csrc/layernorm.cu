@@ -246,29 +246,14 @@ static int ln_bwd_dispatch(const void* dy_bf16, const float* dy_f32, const float
   return -1;
 }
 
-extern "C" int b200_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
-                                  float* mean, float* rstd, int rows, int dim, float eps, void* stream) {
-  return ln_fwd_dispatch(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, 0.f, 0u, stream);
+extern "C" int b200_layernorm_fwd(const B200LayerNormFwdArgs* a, void* stream) {
+  B200_CHECK_STRUCT(a, B200LayerNormFwdArgs, "b200_layernorm_fwd");
+  return ln_fwd_dispatch(a->x, a->gamma, a->beta, a->y_bf16, a->y_f32, a->mean, a->rstd, a->rows, a->dim, a->eps, a->drop_p,
+                         a->drop_seed, stream);
 }
 
-extern "C" int b200_layernorm_fwd_dropout(const float* x, const float* gamma, const float* beta, void* y_bf16,
-                                          float* y_f32, float* mean, float* rstd, int rows, int dim, float eps,
-                                          float drop_p, unsigned int drop_seed, void* stream) {
-  return ln_fwd_dispatch(x, gamma, beta, y_bf16, y_f32, mean, rstd, rows, dim, eps, drop_p, drop_seed, stream);
-}
-
-extern "C" int b200_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* dres_f32, const float* x,
-                                  const float* mean, const float* rstd, const float* gamma, float* dx_f32,
-                                  void* dx_bf16, float* dgamma, float* dbeta, int rows, int dim, void* stream) {
-  return ln_bwd_dispatch(dy_bf16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx_bf16, dgamma, dbeta, rows, dim,
-                         0.f, 0u, 0.f, 0u, stream);
-}
-
-extern "C" int b200_layernorm_bwd_dropout(const void* dy_bf16, const float* dy_f32, const float* dres_f32,
-                                          const float* x, const float* mean, const float* rstd, const float* gamma,
-                                          float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, int rows, int dim,
-                                          float in_p, unsigned int in_seed, float out_p, unsigned int out_seed,
-                                          void* stream) {
-  return ln_bwd_dispatch(dy_bf16, dy_f32, dres_f32, x, mean, rstd, gamma, dx_f32, dx_bf16, dgamma, dbeta, rows, dim,
-                         in_p, in_seed, out_p, out_seed, stream);
+extern "C" int b200_layernorm_bwd(const B200LayerNormBwdArgs* a, void* stream) {
+  B200_CHECK_STRUCT(a, B200LayerNormBwdArgs, "b200_layernorm_bwd");
+  return ln_bwd_dispatch(a->dy_bf16, a->dy_f32, a->dres_f32, a->x, a->mean, a->rstd, a->gamma, a->dx_f32, a->dx_bf16,
+                         a->dgamma, a->dbeta, a->rows, a->dim, a->in_p, a->in_seed, a->out_p, a->out_seed, stream);
 }

@@ -165,7 +165,8 @@ sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
-// out[0] = sum of squares, out[1] = norm, out[2] = clip coefficient min(1, max_norm / (norm + 1e-6)) (1 if max_norm <= 0)
+// out[0] = sum of squares, out[1] = norm, out[2] = clip coefficient min(1, max_norm / (norm + 1e-6)) (1 if max_norm <= 0),
+// out[3] += 1 when the norm is finite: the number of optimizer updates really applied (kept by the caller across steps)
 __global__ void sumsq_final_kernel(const float* __restrict__ partial, float* __restrict__ out, float max_norm,
                                    float pre_scale) {
   __shared__ double red[SUMSQ_THREADS];
@@ -183,6 +184,7 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partial, float* __r
     out[0] = (float)ss;
     out[1] = norm;
     out[2] = (max_norm > 0.f) ? fminf(1.0f, max_norm / (norm + 1e-6f)) : 1.0f;
+    if (isfinite(out[0])) out[3] += 1.0f;
   }
 }
 
@@ -199,11 +201,24 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
              const float* __restrict__ norm_stats, float grad_scale, float lr, float beta1, float beta2, float eps,
              float bc1, float bc2, int zero_grad) {
   float coef = grad_scale;
-  if (norm_stats) {
-    if (!isfinite(norm_stats[0])) return;   // GradScaler semantics: skip the step on non-finite gradients
-    coef *= norm_stats[2];
-  }
   const long long n4 = n / 4;
+  if (norm_stats) {
+    if (!isfinite(norm_stats[0])) {
+      // GradScaler semantics (timm NativeScaler, task_cruller_pretrain.py:259-268): a non-finite gradient skips the
+      // parameter / moment update. The gradients are still cleared -- the reference calls optimizer.zero_grad() right
+      // after (:295) -- otherwise the NaN / Inf would stay in the accumulate-only arena and poison every later step.
+      if (zero_grad)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+          reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+    coef *= norm_stats[2];
+    // bias corrections from the number of updates really applied (skipped steps do not count, as in torch.optim.AdamW
+    // whose state['step'] only advances inside step())
+    const double st = (double)norm_stats[3];
+    bc1 = (float)(1.0 - pow((double)beta1, st));
+    bc2 = (float)(1.0 - pow((double)beta2, st));
+  }
   const float inv_bc1 = 1.0f / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
@@ -275,34 +290,34 @@ extern "C" int b200_ce_fwd_bwd(const void* logits_bf16, long long ld, const long
   return 0;
 }
 
-extern "C" int b200_grad_norm(const float* grads, long long n, float* workspace, float* out3, float max_norm,
+extern "C" int b200_grad_norm(const float* grads, long long n, float* workspace, float* out4, float max_norm,
                               float pre_scale, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  B200_CHECK_ARG(grads && workspace && out3 && n > 0, "b200_grad_norm: bad arguments");
+  B200_CHECK_ARG(grads && workspace && out4 && n > 0, "b200_grad_norm: bad arguments");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(grads) & 15) == 0, "b200_grad_norm: grads must be 16-byte aligned");
   sumsq_partial_kernel<<<SUMSQ_BLOCKS, SUMSQ_THREADS, 0, s>>>(grads, n, workspace);
   B200_CHECK_LAUNCH("sumsq_partial");
-  sumsq_final_kernel<<<1, SUMSQ_THREADS, 0, s>>>(workspace, out3, max_norm, pre_scale);
+  sumsq_final_kernel<<<1, SUMSQ_THREADS, 0, s>>>(workspace, out4, max_norm, pre_scale);
   B200_CHECK_LAUNCH("sumsq_final");
   return 0;
 }
 
 extern "C" int b200_grad_norm_workspace_floats(void) { return SUMSQ_BLOCKS; }
 
-extern "C" int b200_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16,
-                               long long n, const void* segments, int num_segments, const float* norm_stats,
-                               float grad_scale, float lr, float beta1, float beta2, float eps, int step,
-                               int zero_grad, void* stream) {
+extern "C" int b200_adamw_step(const B200AdamWArgs* a, void* stream) {
+  B200_CHECK_STRUCT(a, B200AdamWArgs, "b200_adamw_step");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  B200_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && segments && num_segments > 0 && n > 0 && step > 0,
+  B200_CHECK_ARG(a->params && a->grads && a->exp_avg && a->exp_avg_sq && a->segments && a->num_segments > 0 && a->n > 0,
                  "b200_adamw_step: bad arguments");
-  B200_CHECK_ARG(n % 4 == 0, "b200_adamw_step: arena length must be a multiple of 4");
-  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-  const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+  B200_CHECK_ARG(a->norm_stats != nullptr || a->step > 0, "b200_adamw_step: step must be >= 1 when norm_stats is NULL");
+  B200_CHECK_ARG(a->n % 4 == 0, "b200_adamw_step: arena length must be a multiple of 4");
+  const int step = a->step > 0 ? a->step : 1;      // (ignored when norm_stats carries the device-side update counter)
+  const float bc1 = (float)(1.0 - pow((double)a->beta1, (double)step));
+  const float bc2 = (float)(1.0 - pow((double)a->beta2, (double)step));
   int grid = num_sms() * 8;
-  adamw_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, reinterpret_cast<bf16*>(params_bf16), n,
-                                    reinterpret_cast<const AdamSeg*>(segments), num_segments, norm_stats, grad_scale,
-                                    lr, beta1, beta2, eps, bc1, bc2, zero_grad);
+  adamw_kernel<<<grid, 256, 0, s>>>(a->params, a->grads, a->exp_avg, a->exp_avg_sq, reinterpret_cast<bf16*>(a->params_bf16),
+                                    a->n, reinterpret_cast<const AdamSeg*>(a->segments), a->num_segments, a->norm_stats,
+                                    a->grad_scale, a->lr, a->beta1, a->beta2, a->eps, bc1, bc2, a->zero_grad);
   B200_CHECK_LAUNCH("adamw_step");
   return 0;
 }

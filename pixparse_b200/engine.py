@@ -141,8 +141,10 @@ class CrullerEngine:
         self._shadow_fresh = False
         self._param_versions = None
         # dropout: live in training mode exactly where BartDecoder applies it (the ViT has all drop rates 0);
-        # masks are regenerated from (seed, site) in backward, the seed advances every forward
-        self.dropout_seed = 0x5EED
+        # masks are regenerated from (seed, site) in backward, the seed advances every forward. The per-engine seed is
+        # drawn from torch's default generator (torch.manual_seed controls it; framework/random.py seeds every rank with
+        # seed + rank, so DDP ranks draw different masks) the first time a training forward needs it.
+        self.dropout_seed = None
         self._dropout_calls = 0
 
     # ------------------------------------------------------------------------------------------------ binding
@@ -220,7 +222,12 @@ class CrullerEngine:
         return [p._version for p in self.arena.params]
 
     def refresh_shadow(self, force=False):
-        """bf16 shadow weights follow the fp32 masters (one cast kernel over the arena)."""
+        """bf16 shadow weights follow the fp32 masters (one cast kernel over the arena).
+
+        The cast runs when a Parameter's version counter moved (optimizer.step of a torch optimizer, load_state_dict,
+        p.copy_ / p.add_ under no_grad ...) or after the fused optimizer reported an update. Writers that bypass the
+        version counter -- ``p.data.copy_()``, EMA swaps through ``.data``, a collective writing ``arena.p32`` -- must call
+        ``refresh_shadow(force=True)`` (or ``invalidate_shadow()``) themselves; there is no way to observe them."""
         ar = self.ensure_bound()
         ver = self._versions()
         if force or not self._shadow_fresh or ver != self._param_versions:
@@ -230,6 +237,10 @@ class CrullerEngine:
                 self._patch_w16[:, :self._patch_k].copy_(ar.w16("vit.patch.w", (D, self._patch_k)))
             self._shadow_fresh = True
             self._param_versions = ver
+
+    def invalidate_shadow(self):
+        """Mark the bf16 shadow stale: the next forward re-casts the fp32 masters (for writers that go through ``.data``)."""
+        self._shadow_fresh = False
 
     def mark_params_updated_by_kernel(self, shadow_written):
         """Called by the fused optimizer: masters changed through raw pointers (no torch version bump)."""
@@ -301,6 +312,7 @@ class CrullerEngine:
         x, meanf, rstdf = st.final
         dx32, dx16 = ops.layernorm_bwd(x, meanf, rstdf, ar.w32("vit.norm.w"), ar.grad("vit.norm.w"),
                                        ar.grad("vit.norm.b"), dy32=d_enc32)
+        # Bias gradients ride on the weight-gradient GEMMs (their A operand is dY: B200GemmArgs.bias_grad), no colsum pass.
         # Weight / bias gradients have no consumer before the optimizer, so they can run on a side stream and fill the
         # partially empty last waves of the main stream's persistent kernels (opt-in: PIXPARSE_B200_SIDE_WGRAD=1).
         side = self._side_stream() if self.side_wgrad and dx16.is_cuda else None
@@ -339,15 +351,15 @@ class CrullerEngine:
             (x0, mean1, rstd1, ln1, qkv, attn, lse, x1, mean2, rstd2, ln2, hpre, g) = st.blocks[i]
             # --- MLP
             def w_fc2(dx16=dx16, g=g, k=k):
-                ops.gemm(dx16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"))
-                ops.colsum(dx16, ar.grad(k + "fc2.b"))
+                ops.gemm(dx16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"),
+                         bias_grad=ar.grad(k + "fc2.b"))
             at_start = mark()           # dx16 of this block is complete here
             d_h = ops.gemm(dx16, ar.w16(k + "fc2.w"), b_mn=True, epi=EPI_DGELU_BF16, aux=hpre)
             ev_fc2 = on_side(w_fc2, (dx16, g), after=at_start)      # main-stream kernel first: it is the critical path
 
             def w_fc1(d_h=d_h, ln2=ln2, k=k):
-                ops.gemm(d_h, ln2, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"))
-                ops.colsum(d_h, ar.grad(k + "fc1.b"))
+                ops.gemm(d_h, ln2, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"),
+                         bias_grad=ar.grad(k + "fc1.b"))
             d_ln2 = ops.gemm(d_h, ar.w16(k + "fc1.w"), b_mn=True)
             on_side(w_fc1, (d_h, ln2))
             wait(ev_fc2)                # the LayerNorm backward below overwrites dx16
@@ -355,8 +367,8 @@ class CrullerEngine:
                               dy16=d_ln2, dres32=dx32, dx32=dx32, dx16=dx16)
             # --- attention
             def w_proj(dx16=dx16, attn=attn, k=k):
-                ops.gemm(dx16, attn, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "proj.w"))
-                ops.colsum(dx16, ar.grad(k + "proj.b"))
+                ops.gemm(dx16, attn, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "proj.w"),
+                         bias_grad=ar.grad(k + "proj.b"))
             at_ln2 = mark()
             d_attn = ops.gemm(dx16, ar.w16(k + "proj.w"), b_mn=True)
             ev_proj = on_side(w_proj, (dx16, attn), after=at_ln2)
@@ -365,8 +377,8 @@ class CrullerEngine:
                               q_col0=0, k_col0=D, v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D)
 
             def w_qkv(dqkv=dqkv, ln1=ln1, k=k):
-                ops.gemm(dqkv, ln1, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "qkv.w"))
-                ops.colsum(dqkv, ar.grad(k + "qkv.b"))
+                ops.gemm(dqkv, ln1, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "qkv.w"),
+                         bias_grad=ar.grad(k + "qkv.b"))
             d_ln1 = ops.gemm(dqkv, ar.w16(k + "qkv.w"), b_mn=True)
             on_side(w_qkv, (dqkv, ln1))
             wait(ev_proj)               # dx16 is overwritten again
@@ -385,9 +397,8 @@ class CrullerEngine:
                               ar.grad("vit.norm_pre.b"), dy32=dx32, dx32=dx32, want_bf16=False)
         dproj = ops.tokens_assemble_bwd(dx32, ar.grad("vit.cls_token"), ar.grad("vit.pos_embed"), B, S, D)
         ops.gemm(dproj, st.patches, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
-                 out=ar.grad("vit.patch.w", (D, self._patch_k)), N=self._patch_k)
-        if "vit.patch.b" in ar.index:
-            ops.colsum(dproj, ar.grad("vit.patch.b"))
+                 out=ar.grad("vit.patch.w", (D, self._patch_k)), N=self._patch_k,
+                 bias_grad=ar.grad("vit.patch.b") if "vit.patch.b" in ar.index else None)
 
     # ------------------------------------------------------------------------------------------------ decoder
     class _Drop:
@@ -401,7 +412,20 @@ class CrullerEngine:
             self.base = int(base_seed) & 0xFFFFFFFF
 
         def _seed(self, site):
-            return (self.base * 2654435761 + site * 40503 + 12345) & 0xFFFFFFFF
+            # murmur3 finaliser over (forward counter, site): the kernels combine the seed LINEARLY with the element
+            # counter (x = pair * 0x9E3779B1 + seed, common.cuh dropout_hash), so seeds that are affine in the step or
+            # the site would make one mask a shifted copy of another; a full-avalanche mix removes that structure
+            x = (self.base ^ (site * 0x9E3779B1)) & 0xFFFFFFFF
+            x ^= x >> 16
+            x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+            x ^= x >> 13
+            x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+            x ^= x >> 16
+            x = (x + 0x27D4EB2F * (site + 1)) & 0xFFFFFFFF
+            x ^= x >> 15
+            x = (x * 0x2C1B3C6D) & 0xFFFFFFFF
+            x ^= x >> 12
+            return x
 
         def emb(self):
             return (self.p, self._seed(0))
@@ -411,10 +435,12 @@ class CrullerEngine:
             p = (self.pa, self.p, self.pa, self.p, self.pact, self.p)[k]
             return (p, self._seed(1 + 8 * layer + k))
 
-    def decoder_forward(self, ids, enc16, B, S, save, cache=None):
+    def decoder_forward(self, ids, enc16, B, S, save, cache=None, key_mask=None):
         """cache: DecodeCache for incremental decoding (inference only): `ids` are the NEW tokens, positions continue
         at cache.length, self-attention keys / values are appended to the cache, the cross-attention K / V projections
-        of the image tokens are computed once and reused."""
+        of the image tokens are computed once and reused.
+        key_mask: uint8 [B, past + T], 0 = padding key hidden from the decoder self-attention (the reference's
+        attention_mask = input_ids.ne(pad), text_decoder_hf.py:68); inference only."""
         ar, bart = self.arena, self.bart
         cfg = bart.config
         D, Hh, nl = cfg.d_model, cfg.decoder_attention_heads, cfg.decoder_layers
@@ -424,6 +450,7 @@ class CrullerEngine:
         past = cache.length if cache is not None else 0
         assert past + T <= cfg.max_position_embeddings, "sequence longer than max_position_embeddings"
         assert not (save and cache is not None), "the KV cache is an inference-only path"
+        assert not (save and key_mask is not None), "attention_mask is honoured on the inference path only"
         M = B * T
         V = ar.index["dec.tok"][2][0]
         if ids.dtype != torch.int64 or not ids.is_contiguous():
@@ -431,7 +458,12 @@ class CrullerEngine:
         st = _Saved()
         st.B, st.T, st.S, st.V, st.ids = B, T, S, V, ids
         self._dropout_calls += 1
-        dr = CrullerEngine._Drop(cfg, self.dropout_seed + 7919 * self._dropout_calls, save and bart.training)
+        training = bool(save and bart.training)
+        if training and self.dropout_seed is None:
+            rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+            self.dropout_seed = (int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) + 0x632BE5AB * rank) & 0xFFFFFFFF
+        dr = CrullerEngine._Drop(cfg, ((self.dropout_seed or 0) * 0x9E3779B1 + self._dropout_calls * 0x85EBCA77) & 0xFFFFFFFF,
+                                 training)
         st.drop = dr
         x_emb = ops.embed_fwd(ids, ar.w32("dec.tok"), ar.w32("dec.pos"), pos_offset=2 + past, scale=1.0)
         h16, h32, me, re_ = ops.layernorm_fwd(x_emb, ar.w32("dec.ln_emb.w"), ar.w32("dec.ln_emb.b"), eps, want_f32=True,
@@ -451,10 +483,10 @@ class CrullerEngine:
                 kv2d = kvbuf.view(B * cache.t_max, 2 * D)
                 a_s, lse_s = ops.attention_fwd(qkv, kv2d, kv2d, B=B, H=Hh, Sq=T, Sk=past + T, q_col0=0, k_col0=0,
                                                v_col0=D, causal=True, q_bs=T * 3 * D, kv_bs=cache.t_max * 2 * D,
-                                               out_bs=T * D, want_lse=False)
+                                               out_bs=T * D, want_lse=False, key_mask=key_mask)
             else:
                 a_s, lse_s = ops.attention_fwd(qkv, qkv, qkv, B=B, H=Hh, Sq=T, Sk=T, q_col0=0, k_col0=D,
-                                               v_col0=2 * D, causal=True, drop=dr.site(j, 0))
+                                               v_col0=2 * D, causal=True, drop=dr.site(j, 0), key_mask=key_mask)
             u1 = torch.empty_like(h32)
             ops.gemm(a_s, ar.w16(k + "sa.o.w"), bias=ar.w32(k + "sa.o.b"), epi=EPI_RESID_F32, aux=h32, out=u1,
                      drop=dr.site(j, 1))
@@ -530,40 +562,40 @@ class CrullerEngine:
             du32, du16 = ops.layernorm_bwd(u3, m3, r3, ar.w32(k + "f_ln.w"), ar.grad(k + "f_ln.w"),
                                            ar.grad(k + "f_ln.b"), dy16=dy16, dy32=dy32, out_drop=dr.site(j, 5))
             d_h = ops.gemm(du16, ar.w16(k + "fc2.w"), b_mn=True, epi=EPI_DGELU_BF16, aux=hpre, drop=dr.site(j, 4))
-            ops.gemm(du16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"))
-            ops.colsum(du16, ar.grad(k + "fc2.b"))
+            ops.gemm(du16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"),
+                     bias_grad=ar.grad(k + "fc2.b"))
             d_h2 = ops.gemm(d_h, ar.w16(k + "fc1.w"), b_mn=True)
-            ops.gemm(d_h, h2_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"))
-            ops.colsum(d_h, ar.grad(k + "fc1.b"))
+            ops.gemm(d_h, h2_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"),
+                     bias_grad=ar.grad(k + "fc1.b"))
             # cross-attention LN
             du32, du16 = ops.layernorm_bwd(u2, m2, r2, ar.w32(k + "ca_ln.w"), ar.grad(k + "ca_ln.w"),
                                            ar.grad(k + "ca_ln.b"), dy16=d_h2, dy32=du32, dx32=du32, dx16=du16,
                                            out_drop=dr.site(j, 3))
             d_ac = ops.gemm(du16, ar.w16(k + "ca.o.w"), b_mn=True)
-            ops.gemm(du16, a_c, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.o.w"))
-            ops.colsum(du16, ar.grad(k + "ca.o.b"))
+            ops.gemm(du16, a_c, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.o.w"),
+                     bias_grad=ar.grad(k + "ca.o.b"))
             dqc = torch.empty_like(qc)
             dkvc = torch.empty_like(kvc)
             ops.attention_bwd(qc, kvc, kvc, a_c, d_ac, lse_c, dqc, dkvc, dkvc, B=B, H=Hh, Sq=T, Sk=S, q_col0=0,
                               k_col0=0, v_col0=D, dq_col0=0, dk_col0=0, dv_col0=D, drop=dr.site(j, 2))
             d_h1 = ops.gemm(dqc, ar.w16(k + "ca.q.w"), b_mn=True)
-            ops.gemm(dqc, h1_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.q.w"))
-            ops.colsum(dqc, ar.grad(k + "ca.q.b"))
+            ops.gemm(dqc, h1_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.q.w"),
+                     bias_grad=ar.grad(k + "ca.q.b"))
             wkv = ar.span(k + "ca.k.w", k + "ca.v.w", "w16").view(2 * D, D)
             if d_enc32 is None:
                 d_enc32 = ops.gemm(dkvc, wkv, b_mn=True, epi=EPI_STORE_F32)
             else:
                 ops.gemm(dkvc, wkv, b_mn=True, epi=EPI_RESID_F32, aux=d_enc32, out=d_enc32)
             ops.gemm(dkvc, enc16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
-                     out=ar.span(k + "ca.k.w", k + "ca.v.w", "grad").view(2 * D, D))
-            ops.colsum(dkvc, ar.span(k + "ca.k.b", k + "ca.v.b", "grad"))
+                     out=ar.span(k + "ca.k.w", k + "ca.v.w", "grad").view(2 * D, D),
+                     bias_grad=ar.span(k + "ca.k.b", k + "ca.v.b", "grad"))
             # self-attention LN
             du32, du16 = ops.layernorm_bwd(u1, m1, r1, ar.w32(k + "sa_ln.w"), ar.grad(k + "sa_ln.w"),
                                            ar.grad(k + "sa_ln.b"), dy16=d_h1, dy32=du32, dx32=du32, dx16=du16,
                                            out_drop=dr.site(j, 1))
             d_as = ops.gemm(du16, ar.w16(k + "sa.o.w"), b_mn=True)
-            ops.gemm(du16, a_s, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "sa.o.w"))
-            ops.colsum(du16, ar.grad(k + "sa.o.b"))
+            ops.gemm(du16, a_s, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "sa.o.w"),
+                     bias_grad=ar.grad(k + "sa.o.b"))
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv, qkv, qkv, a_s, d_as, lse_s, dqkv, dqkv, dqkv, B=B, H=Hh, Sq=T, Sk=T, q_col0=0,
                               k_col0=D, v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D, causal=True,
@@ -571,8 +603,8 @@ class CrullerEngine:
             wqkv = ar.span(k + "sa.q.w", k + "sa.v.w", "w16").view(3 * D, D)
             dy16 = ops.gemm(dqkv, wqkv, b_mn=True)
             ops.gemm(dqkv, h0_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
-                     out=ar.span(k + "sa.q.w", k + "sa.v.w", "grad").view(3 * D, D))
-            ops.colsum(dqkv, ar.span(k + "sa.q.b", k + "sa.v.b", "grad"))
+                     out=ar.span(k + "sa.q.w", k + "sa.v.w", "grad").view(3 * D, D),
+                     bias_grad=ar.span(k + "sa.q.b", k + "sa.v.b", "grad"))
             dy32 = du32
             st.layers[j] = None
         x_emb, me, re_ = st.emb
@@ -603,8 +635,9 @@ class CrullerEngine:
                       use_cache=False):
         """TextDecoderHf.forward (teacher-forced / greedy step): logits (B, T, V) bf16 [, DecodeCache].
 
-        attention_mask: the reference builds it as input_ids != pad (text_decoder_hf.py:68). With right padding and a
-        causal mask PAD keys can only influence PAD queries, so it does not change any non-pad position.
+        attention_mask: (B, past + T), 0 = padding; the reference builds it as input_ids.ne(pad)
+        (text_decoder_hf.py:68) and HF combines it with the causal mask of the decoder SELF-attention: a pad token inside
+        the prefix (greedy decoding can emit id 1) is hidden from every later query. Cross-attention is unmasked.
         use_cache / past_key_values: the incremental path of prepare_inputs_for_inference (text_decoder_hf.py:69-70):
         only the new tokens are passed, keys / values of the prefix come from the cache."""
         self.refresh_shadow()
@@ -617,7 +650,13 @@ class CrullerEngine:
         if cache is None and use_cache:
             cfg = self.bart.config
             cache = DecodeCache(cfg.decoder_layers, B, cfg.max_position_embeddings, cfg.d_model, enc16.device)
-        logits, _ = self.decoder_forward(input_ids, enc16, B, S, save=False, cache=cache)
+        key_mask = None
+        if attention_mask is not None:
+            past = cache.length if cache is not None else 0
+            assert attention_mask.shape == (B, past + input_ids.shape[1]), \
+                f"attention_mask {tuple(attention_mask.shape)} must cover the {past} cached + {input_ids.shape[1]} new tokens"
+            key_mask = attention_mask.to(device=enc16.device, dtype=torch.uint8).contiguous()
+        logits, _ = self.decoder_forward(input_ids, enc16, B, S, save=False, cache=cache, key_mask=key_mask)
         V = self.arena.index["dec.tok"][2][0]
         logits = logits.view(B, input_ids.shape[1], -1)[:, :, :V]
         return (logits, cache) if (use_cache or past_key_values is not None) else logits

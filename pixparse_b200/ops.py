@@ -20,10 +20,13 @@ def _ld(t):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=None, bias=None, aux=None,
-         splits=0, block_n=0, M=None, N=None, K=None, drop=None):
+         splits=0, block_n=0, M=None, N=None, K=None, drop=None, bias_grad=None):
     """D[M,N] = sum_k A(m,k) B(n,k) on the tcgen05 path.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16;  b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
+    drop = (p, seed): dropout fused into the RESID / GELU / DGELU epilogue.
+    bias_grad (weight gradients only: epi=EPI_REDUCE_F32, a_mn=True): fp32 [M] vector that receives += the column sums
+    of dY (the A operand), i.e. the nn.Linear bias gradient, without another pass over dY.
     """
     assert a.dtype == BF16 and b.dtype == BF16
     if M is None:
@@ -41,20 +44,23 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=Non
             out = torch.zeros((M, N), device=a.device, dtype=F32)
         else:
             out = torch.empty((M, N), device=a.device, dtype=BF16)
-    if drop is not None and drop[0] > 0.0:     # drop = (p, seed): dropout fused into the epilogue
-        call("b200_gemm_bf16_dropout", ptr(a), _ld(a), int(a_mn), ptr(b), _ld(b), int(b_mn), M, N, K, epi,
-             ptr(out), _ld(out), ptr(out2), _ld(out2) if out2 is not None else 0, ptr(bias),
-             ptr(aux), _ld(aux) if aux is not None else 0, splits, block_n, float(drop[0]), int(drop[1]), stream())
-        return out
-    call("b200_gemm_bf16", ptr(a), _ld(a), int(a_mn), ptr(b), _ld(b), int(b_mn), M, N, K, epi,
-         ptr(out), _ld(out), ptr(out2), _ld(out2) if out2 is not None else 0, ptr(bias),
-         ptr(aux), _ld(aux) if aux is not None else 0, splits, block_n, stream())
+    if bias_grad is not None:
+        assert bias_grad.dtype == F32 and bias_grad.numel() >= M
+    p, seed = drop if (drop is not None and drop[0] > 0.0) else (0.0, 0)
+    args = _lib.GemmArgs(epilogue=epi, a=ptr(a), lda=_ld(a), a_mn_major=int(a_mn), b=ptr(b), ldb=_ld(b),
+                         b_mn_major=int(b_mn), m=M, n=N, k=K, out=ptr(out), ldo=_ld(out), out2=ptr(out2),
+                         ldo2=_ld(out2) if out2 is not None else 0, bias=ptr(bias), aux=ptr(aux),
+                         ld_aux=_ld(aux) if aux is not None else 0, bias_grad=ptr(bias_grad), splits=splits,
+                         block_n=block_n, drop_p=float(p), drop_seed=int(seed))
+    call("b200_gemm_bf16", args, stream())
     return out
 
 
 def attention_fwd(q, k, v, *, B, H, Sq, Sk, q_col0=0, k_col0=0, v_col0=0, causal=False, scale=None, out=None,
-                  lse=None, drop=None, q_bs=0, kv_bs=0, out_bs=0, want_lse=True):
-    """q/k/v: 2-D bf16 views [B*S, row_width]; head h lives at columns [col0 + 64h, col0 + 64h + 64)."""
+                  lse=None, drop=None, q_bs=0, kv_bs=0, out_bs=0, want_lse=True, key_mask=None):
+    """q/k/v: 2-D bf16 views [B*S, row_width]; head h lives at columns [col0 + 64h, col0 + 64h + 64).
+    q_bs / kv_bs / out_bs: explicit batch strides in elements (KV cache), 0 = dense [B, S, ld].
+    key_mask: optional uint8 / bool [B, >= Sk] (row stride = its stride(0)), 0 = key hidden (decoder attention_mask)."""
     dh = 64
     if scale is None:
         scale = dh ** -0.5
@@ -62,17 +68,18 @@ def attention_fwd(q, k, v, *, B, H, Sq, Sk, q_col0=0, k_col0=0, v_col0=0, causal
         out = torch.empty((B * Sq, H * dh), device=q.device, dtype=BF16)
     if lse is None and want_lse:
         lse = torch.empty((B, H, Sq), device=q.device, dtype=F32)
-    if q_bs or kv_bs or out_bs:      # explicit batch strides (KV cache): token stride = row stride of the 2-D view
-        call("b200_attention_fwd_strided", ptr(q), _ld(q), q_bs, q_col0, ptr(k), _ld(k), kv_bs, k_col0, ptr(v), _ld(v),
-             kv_bs, v_col0, ptr(out), _ld(out), out_bs, ptr(lse), B, H, Sq, Sk, dh, int(causal), float(scale), stream())
-        return out, lse
-    if drop is not None and drop[0] > 0.0:
-        call("b200_attention_fwd_dropout", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
-             ptr(out), _ld(out), ptr(lse), B, H, Sq, Sk, dh, int(causal), float(scale), float(drop[0]), int(drop[1]),
-             stream())
-        return out, lse
-    call("b200_attention_fwd", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
-         ptr(out), _ld(out), ptr(lse), B, H, Sq, Sk, dh, int(causal), float(scale), stream())
+    p, seed = drop if (drop is not None and drop[0] > 0.0) else (0.0, 0)
+    km_bs = 0
+    if key_mask is not None:
+        assert key_mask.dim() == 2 and key_mask.stride(1) == 1 and key_mask.shape[1] >= Sk
+        assert key_mask.dtype in (torch.uint8, torch.bool)
+        km_bs = key_mask.stride(0)
+    args = _lib.AttentionFwdArgs(batch=B, q=ptr(q), ldq=_ld(q), q_bstride=q_bs, q_col0=q_col0, k_col0=k_col0, k=ptr(k),
+                                 ldk=_ld(k), k_bstride=kv_bs, v=ptr(v), ldv=_ld(v), v_bstride=kv_bs, v_col0=v_col0,
+                                 heads=H, out=ptr(out), ld_out=_ld(out), out_bstride=out_bs, lse=ptr(lse),
+                                 key_mask=ptr(key_mask), key_mask_bstride=km_bs, sq=Sq, sk=Sk, head_dim=dh,
+                                 causal=int(causal), scale=float(scale), drop_p=float(p), drop_seed=int(seed))
+    call("b200_attention_fwd", args, stream())
     return out, lse
 
 
@@ -91,15 +98,14 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, q_col0=0, k
     if ws is None or ws.numel() < need:
         ws = torch.empty((need,), device=q.device, dtype=torch.uint8)
         _att_ws[key] = ws
-    if drop is not None and drop[0] > 0.0:
-        call("b200_attention_bwd_dropout", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
-             ptr(o), _ld(o), ptr(d_o), _ld(d_o), do_col0, ptr(lse), ptr(dq), _ld(dq), dq_col0, ptr(dk), _ld(dk),
-             dk_col0, ptr(dv), _ld(dv), dv_col0, ptr(ws), B, H, Sq, Sk, dh, int(causal), float(scale), float(drop[0]),
-             int(drop[1]), stream())
-        return dq, dk, dv
-    call("b200_attention_bwd", ptr(q), _ld(q), q_col0, ptr(k), _ld(k), k_col0, ptr(v), _ld(v), v_col0,
-         ptr(o), _ld(o), ptr(d_o), _ld(d_o), do_col0, ptr(lse), ptr(dq), _ld(dq), dq_col0, ptr(dk), _ld(dk), dk_col0,
-         ptr(dv), _ld(dv), dv_col0, ptr(ws), B, H, Sq, Sk, dh, int(causal), float(scale), stream())
+    p, seed = drop if (drop is not None and drop[0] > 0.0) else (0.0, 0)
+    args = _lib.AttentionBwdArgs(batch=B, q=ptr(q), ldq=_ld(q), k=ptr(k), ldk=_ld(k), v=ptr(v), ldv=_ld(v),
+                                 q_col0=q_col0, k_col0=k_col0, v_col0=v_col0, do_col0=do_col0, o=ptr(o), ld_o=_ld(o),
+                                 d_o=ptr(d_o), ld_do=_ld(d_o), lse=ptr(lse), dq=ptr(dq), ld_dq=_ld(dq), dk=ptr(dk),
+                                 ld_dk=_ld(dk), dv=ptr(dv), ld_dv=_ld(dv), dq_col0=dq_col0, dk_col0=dk_col0,
+                                 dv_col0=dv_col0, heads=H, workspace=ptr(ws), sq=Sq, sk=Sk, head_dim=dh,
+                                 causal=int(causal), scale=float(scale), drop_p=float(p), drop_seed=int(seed))
+    call("b200_attention_bwd", args, stream())
     return dq, dk, dv
 
 
@@ -110,12 +116,11 @@ def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False, drop=N
     y32 = torch.empty((rows, dim), device=x.device, dtype=F32) if want_f32 else None
     mean = torch.empty((rows,), device=x.device, dtype=F32)
     rstd = torch.empty((rows,), device=x.device, dtype=F32)
-    if drop is not None and drop[0] > 0.0:
-        call("b200_layernorm_fwd_dropout", ptr(x), ptr(gamma), ptr(beta), ptr(y16), ptr(y32), ptr(mean), ptr(rstd),
-             rows, dim, float(eps), float(drop[0]), int(drop[1]), stream())
-        return y16, y32, mean, rstd
-    call("b200_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(y16), ptr(y32), ptr(mean), ptr(rstd), rows, dim,
-         float(eps), stream())
+    p, seed = drop if (drop is not None and drop[0] > 0.0) else (0.0, 0)
+    args = _lib.LayerNormFwdArgs(rows=rows, x=ptr(x), gamma=ptr(gamma), beta=ptr(beta), y_bf16=ptr(y16), y_f32=ptr(y32),
+                                 mean=ptr(mean), rstd=ptr(rstd), dim=dim, eps=float(eps), drop_p=float(p),
+                                 drop_seed=int(seed))
+    call("b200_layernorm_fwd", args, stream())
     return y16, y32, mean, rstd
 
 
@@ -126,17 +131,13 @@ def layernorm_bwd(x, mean, rstd, gamma, dgamma, dbeta, *, dy16=None, dy32=None, 
         dx32 = torch.empty((rows, dim), device=x.device, dtype=F32)
     if dx16 is None and want_bf16:
         dx16 = torch.empty((rows, dim), device=x.device, dtype=BF16)
-    i_on = in_drop is not None and in_drop[0] > 0.0
-    o_on = out_drop is not None and out_drop[0] > 0.0
-    if i_on or o_on:
-        ip, iseed = in_drop if i_on else (0.0, 0)
-        op_, oseed = out_drop if o_on else (0.0, 0)
-        call("b200_layernorm_bwd_dropout", ptr(dy16), ptr(dy32), ptr(dres32), ptr(x), ptr(mean), ptr(rstd), ptr(gamma),
-             ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, dim, float(ip), int(iseed), float(op_), int(oseed),
-             stream())
-        return dx32, dx16
-    call("b200_layernorm_bwd", ptr(dy16), ptr(dy32), ptr(dres32), ptr(x), ptr(mean), ptr(rstd), ptr(gamma),
-         ptr(dx32), ptr(dx16), ptr(dgamma), ptr(dbeta), rows, dim, stream())
+    ip, iseed = in_drop if (in_drop is not None and in_drop[0] > 0.0) else (0.0, 0)
+    op_, oseed = out_drop if (out_drop is not None and out_drop[0] > 0.0) else (0.0, 0)
+    args = _lib.LayerNormBwdArgs(rows=rows, dy_bf16=ptr(dy16), dy_f32=ptr(dy32), dres_f32=ptr(dres32), x=ptr(x),
+                                 mean=ptr(mean), rstd=ptr(rstd), gamma=ptr(gamma), dx_f32=ptr(dx32), dx_bf16=ptr(dx16),
+                                 dgamma=ptr(dgamma), dbeta=ptr(dbeta), dim=dim, in_p=float(ip), in_seed=int(iseed),
+                                 out_p=float(op_), out_seed=int(oseed))
+    call("b200_layernorm_bwd", args, stream())
     return dx32, dx16
 
 
@@ -213,22 +214,29 @@ _norm_ws = {}
 
 
 def grad_norm(grads, max_norm=0.0, pre_scale=1.0, out=None):
-    """Deterministic global L2 norm of a flat fp32 arena. out = [sumsq, norm, clip_coef]."""
+    """Deterministic global L2 norm of a flat fp32 arena. out = [sumsq, norm, clip_coef, updates]: out[3] is a counter
+    the caller keeps across steps, incremented when the norm is finite (the number of updates really applied)."""
     dev = grads.device
     if dev not in _norm_ws:
         _norm_ws[dev] = torch.empty((_lib.lib().b200_grad_norm_workspace_floats(),), device=dev, dtype=F32)
     if out is None:
-        out = torch.empty((3,), device=dev, dtype=F32)
+        out = torch.zeros((4,), device=dev, dtype=F32)
+    assert out.numel() >= 4
     call("b200_grad_norm", ptr(grads), grads.numel(), ptr(_norm_ws[dev]), ptr(out), float(max_norm or 0.0),
          float(pre_scale), stream())
     return out
 
 
 def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, segments, num_segments, *, lr, beta1, beta2, eps,
-               step, norm_stats=None, grad_scale=1.0, zero_grad=True):
-    call("b200_adamw_step", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), ptr(params_bf16),
-         params.numel(), ptr(segments), num_segments, ptr(norm_stats), float(grad_scale), float(lr), float(beta1),
-         float(beta2), float(eps), int(step), int(zero_grad), stream())
+               step=0, norm_stats=None, grad_scale=1.0, zero_grad=True):
+    """Fused clip + AdamW + bf16 shadow + grad zeroing. With norm_stats (grad_norm's output) the clip coefficient, the
+    step number (norm_stats[3]) and the skip-on-non-finite decision all come from the device; otherwise `step` (>= 1)."""
+    args = _lib.AdamWArgs(num_segments=num_segments, params=ptr(params), grads=ptr(grads), exp_avg=ptr(exp_avg),
+                          exp_avg_sq=ptr(exp_avg_sq), params_bf16=ptr(params_bf16), n=params.numel(),
+                          segments=ptr(segments), norm_stats=ptr(norm_stats), grad_scale=float(grad_scale), lr=float(lr),
+                          beta1=float(beta1), beta2=float(beta2), eps=float(eps), step=int(step),
+                          zero_grad=int(zero_grad))
+    call("b200_adamw_step", args, stream())
 
 
 def release_workspaces():

@@ -59,8 +59,10 @@ class FusedAdamW(torch.optim.Optimizer):
         self.arena = arena
         self.exp_avg = torch.zeros_like(arena.p32)
         self.exp_avg_sq = torch.zeros_like(arena.p32)
-        self._step = 0
-        self.norm_stats = torch.zeros(3, device=arena.device, dtype=torch.float32)
+        self._step = 0      # update ATTEMPTS (host side); the number really applied lives in norm_stats[3]
+        # [sum of squares, global L2 norm, clip coefficient, applied updates] -- written by the grad-norm kernel, read by
+        # the AdamW kernel; nothing here ever comes back to the host inside a step
+        self.norm_stats = torch.zeros(4, device=arena.device, dtype=torch.float32)
         self._segs_key = None
         self._segs = None
         self._nseg = 0
@@ -103,23 +105,35 @@ class FusedAdamW(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, clip_grad_norm=None, grad_scale=1.0):
         """One update over the whole arena. clip_grad_norm: max global L2 norm (timm clip mode 'norm') or None.
-        Gradients are zeroed in the same pass (the reference calls optimizer.zero_grad() right after, :295)."""
+
+        The global gradient norm is always computed: a non-finite norm skips the parameter / moment update exactly as
+        timm's NativeScaler (GradScaler.step) does in the reference (task_cruller_pretrain.py:259-268) -- the skipped
+        step does not advance AdamW's bias-correction step either -- and the decision stays on the device (no host
+        sync). Gradients are zeroed in the same pass, also on a skipped step (the reference calls
+        optimizer.zero_grad() right after, :295)."""
         assert closure is None
         if not self.arena.intact():
             raise RuntimeError("parameters were re-allocated after the optimizer was created; rebuild the optimizer")
         base_lr = self._segments()
         g0 = self.param_groups[0]
         self._step += 1
-        stats = None
-        if clip_grad_norm is not None:
-            stats = ops.grad_norm(self.arena.g32, max_norm=float(clip_grad_norm), pre_scale=float(grad_scale),
-                                  out=self.norm_stats)
+        stats = ops.grad_norm(self.arena.g32, max_norm=float(clip_grad_norm or 0.0), pre_scale=float(grad_scale),
+                              out=self.norm_stats)
         ops.adamw_step(self.arena.p32, self.arena.g32, self.exp_avg, self.exp_avg_sq, self.arena.p16, self._segs,
                        self._nseg, lr=base_lr, beta1=g0['betas'][0], beta2=g0['betas'][1], eps=g0['eps'],
-                       step=self._step, norm_stats=stats, grad_scale=grad_scale, zero_grad=True)
+                       norm_stats=stats, grad_scale=grad_scale, zero_grad=True)
         self.engine.mark_params_updated_by_kernel(True)
+
+    def applied_steps(self):
+        """Number of updates really applied (device -> host read): attempts minus the steps skipped for non-finite
+        gradients. This is what torch.optim.AdamW keeps in state['step']."""
+        return int(self.norm_stats[3].item())
+
+    def state_dict(self):
+        n = float(self.applied_steps())
         for st in self.state.values():
-            st["step"] = torch.tensor(float(self._step))
+            st["step"] = torch.tensor(n)
+        return super().state_dict()
 
     def zero_grad(self, set_to_none=False):
         # gradients live in the arena and were zeroed by step(); keep param.grad attached to the arena views
@@ -136,6 +150,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     self.state[p]["exp_avg"].copy_(sd_state[i]["exp_avg"])
                     self.state[p]["exp_avg_sq"].copy_(sd_state[i]["exp_avg_sq"])
                     self._step = max(self._step, int(sd_state[i]["step"]))
+            self.norm_stats[3] = float(self._step)
         for g, sg in zip(self.param_groups, state_dict["param_groups"]):
             for k, v in sg.items():
                 if k != "params":

@@ -112,3 +112,75 @@ def test_cer_wer_edit_distance():
     assert wer(["the quick brown fox"], ["the quick fox"]) == pytest.approx(0.25)
     assert wer(["a b", "c d"], ["a x", "c d"]) == pytest.approx(0.25)
     assert cer(["<pad>ab  c<pad>"], ["ab c"]) == 0.0       # <pad> removed, whitespace collapsed / stripped
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# loader / sample boundary: LoaderBundle.set_interval, sample layouts, the app/train.py interval loop
+# ---------------------------------------------------------------------------------------------------------------------
+def test_loader_bundle_layouts_and_set_interval():
+    from pixparse_b200 import data
+    b = data.create_synthetic_loader("pretrain", batch_size=2, num_samples=5, image_size=(32, 32), text_len=9, seed=3)
+    assert (b.num_batches, b.num_samples, b.sampler) == (2, 5, None)        # drop_last on the train split
+    batches = list(b.loader)
+    assert len(batches) == 2
+    img, txt, tgt = batches[0]
+    assert img.shape == (2, 1, 32, 32) and txt.shape == (2, 9) and tgt.shape == (2, 9) and txt.dtype == torch.int64
+    assert (tgt[:, 0] == -100).all()
+    b.set_interval(4)
+    assert b.loader.dataset.interval == 4
+    # distributed: a DistributedSampler is created and set_interval re-seeds its shuffle (data/loader.py:95-104)
+    b0 = data.create_synthetic_loader("pretrain", 2, 8, image_size=(32, 32), text_len=9, world_size=2, global_rank=0)
+    b1 = data.create_synthetic_loader("pretrain", 2, 8, image_size=(32, 32), text_len=9, world_size=2, global_rank=1)
+    assert b0.num_samples == 4 and b0.num_batches == 2
+    b0.set_interval(1); b1.set_interval(1)
+    i0, i1 = list(b0.sampler), list(b1.sampler)
+    assert sorted(i0 + i1) == list(range(8))                                # ranks partition the interval's samples
+    b0.set_interval(2)
+    assert list(b0.sampler) != i0                                           # another interval, another order
+    # eval-OCR layout: lists of lists (task_cruller_eval_ocr.py:199-207)
+    e = data.create_synthetic_loader("eval_ocr", 3, 3, image_size=(32, 32), text_len=7, is_train=False)
+    img, texts, targets = next(iter(e.loader))
+    assert img.shape == (3, 1, 32, 32) and len(targets) == 3 and isinstance(targets[0], list)
+    assert torch.stack([t[0] for t in targets]).shape == (3, 7)
+    # on a CPU device the prefetcher is transparent
+    p = data.create_synthetic_loader("pretrain", 2, 4, image_size=(32, 32), text_len=9, device="cpu")
+    assert isinstance(p.loader, data.DevicePrefetcher) and len(list(p.loader)) == 2
+
+
+def test_train_loop_drives_task_like_app_train(tmp_path):
+    """app/train.py:48-67: for each interval set_interval(i), train_one_interval (interval_start, train_step per
+    batch, interval_end), then a checkpoint of task.model.state_dict() on the primary rank."""
+    from pixparse_b200 import data
+
+    class Env:
+        def is_primary(self):
+            return True
+
+    class FakeTask:
+        def __init__(self):
+            self.start_interval, self.num_intervals, self.device_env = 1, 3, Env()
+            self.model = torch.nn.Linear(2, 2)
+            self.log = []
+
+        def train_interval_start(self):
+            self.log.append("start")
+
+        def train_step(self, sample):
+            self.log.append(("step", tuple(sample[0].shape)))
+            return {}
+
+        def train_interval_end(self):
+            self.log.append("end")
+
+    calls = []
+    bundle = data.create_synthetic_loader("pretrain", 2, 4, image_size=(32, 32), text_len=9)
+    orig = bundle.set_interval
+    bundle.set_interval = lambda i: (calls.append(i), orig(i))
+    task = FakeTask()
+    data.train(task, {"train": bundle}, output_checkpoint_dir=str(tmp_path), experiment="exp")
+    assert calls == [1, 2]
+    per_interval = ["start", ("step", (2, 1, 32, 32)), ("step", (2, 1, 32, 32)), "end"]
+    assert task.log == per_interval * 2
+    assert sorted(os.listdir(tmp_path / "exp")) == ["checkpoint-1.pt", "checkpoint-2.pt"]
+    sd = torch.load(tmp_path / "exp" / "checkpoint-2.pt")
+    assert set(sd) == {"weight", "bias"}

@@ -315,8 +315,15 @@ def test_cross_entropy(cuda_lib, rows, V):
     assert rel_err(dl[:, :V], lf.grad) < 4e-3                             # bf16 rounding of the gradient
 
 
-def test_grad_norm_and_adamw(cuda_lib):
+def _segments(rows):
     import numpy as np
+    seg = np.zeros(len(rows), dtype=[("end", "<i8"), ("lr_scale", "<f4"), ("wd", "<f4")])
+    for i, (end, scale, wd) in enumerate(rows):
+        seg[i] = (end, scale, wd)
+    return torch.from_numpy(seg.view(np.uint8).copy()).to(DEV)
+
+
+def test_grad_norm_and_adamw(cuda_lib):
     from pixparse_b200 import ops
     torch.manual_seed(10)
     n = 1 << 20
@@ -327,21 +334,113 @@ def test_grad_norm_and_adamw(cuda_lib):
     p16 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
     pr = p.clone().requires_grad_(True)
     opt = torch.optim.AdamW([pr], lr=3e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.0)
-    seg = np.zeros(1, dtype=[("end", "<i8"), ("lr_scale", "<f4"), ("wd", "<f4")])
-    seg["end"] = n; seg["lr_scale"] = 1.0; seg["wd"] = 0.0
-    segs = torch.from_numpy(seg.view(np.uint8)).to(DEV)
+    segs = _segments([(n, 1.0, 0.0)])
+    stats = torch.zeros(4, device=DEV)       # [sumsq, norm, clip coefficient, applied updates]: kept across steps
     for step in (1, 2, 3):
         g = torch.randn(n, device=DEV) * 0.01
         pr.grad = g.clone()
         total = torch.nn.utils.clip_grad_norm_([pr], 1.0)
         opt.step()
-        stats = ops.grad_norm(g, max_norm=1.0)
+        ops.grad_norm(g, max_norm=1.0, out=stats)
         assert abs(stats[1].item() - total.item()) < 1e-5 * total.item()
-        ops.adamw_step(p, g, m, v, p16, segs, 1, lr=3e-4, beta1=0.9, beta2=0.98, eps=1e-6, step=step,
-                       norm_stats=stats)
+        assert stats[3].item() == step         # the device-side update counter drives the bias corrections
+        ops.adamw_step(p, g, m, v, p16, segs, 1, lr=3e-4, beta1=0.9, beta2=0.98, eps=1e-6, norm_stats=stats)
         assert (p - pr.detach()).abs().max().item() < 2e-6
         assert torch.equal(p16, p.bfloat16())
         assert g.abs().max().item() == 0.0      # zero_grad fused
+
+
+def test_adamw_segments_lr_scale_and_weight_decay(cuda_lib):
+    """Per-tensor {end, lr_scale, weight_decay} table (timm param_groups_layer_decay -> torch.optim.AdamW param groups,
+    task_cruller_pretrain.py:196-203): five segments with distinct lr scales and weight decays, boundaries that are not
+    multiples of the kernel's grid stride, three steps, no clipping (host-supplied step number)."""
+    from pixparse_b200 import ops
+    torch.manual_seed(11)
+    sizes = [64 * 13, 64 * 1001, 64 * 3, 64 * 257, 64 * 64]
+    scales = [0.75 ** 4, 0.75 ** 3, 0.75 ** 2, 0.75, 1.0]
+    wds = [0.0, 0.05, 0.0, 0.02, 0.1]
+    n = sum(sizes)
+    p = torch.randn(n, device=DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    p16 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    ends, refs, groups, o = [], [], [], 0
+    for sz, sc, wd in zip(sizes, scales, wds):
+        t = p[o:o + sz].clone().requires_grad_(True)
+        refs.append(t)
+        groups.append({"params": [t], "lr": 1e-3 * sc, "weight_decay": wd})
+        o += sz
+        ends.append(o)
+    opt = torch.optim.AdamW(groups, lr=1e-3, betas=(0.9, 0.99), eps=1e-6)
+    segs = _segments(list(zip(ends, scales, wds)))
+    for step in (1, 2, 3):
+        g = torch.randn(n, device=DEV) * 0.1
+        o = 0
+        for t, sz in zip(refs, sizes):
+            t.grad = g[o:o + sz].clone()
+            o += sz
+        opt.step()
+        ops.adamw_step(p, g, m, v, p16, segs, len(sizes), lr=1e-3, beta1=0.9, beta2=0.99, eps=1e-6, step=step)
+        ref = torch.cat([t.detach() for t in refs])
+        assert (p - ref).abs().max().item() < 3e-6, step
+        # every segment really got its own scale: undoing the update with a neighbour's scale must not match
+        assert torch.equal(p16, p.bfloat16())
+    o = 0
+    for t, sz, sc in zip(refs, sizes, scales):      # per-segment check with a tolerance far below the scale differences
+        assert (p[o:o + sz] - t.detach()).abs().max().item() < 3e-6
+        o += sz
+
+
+def test_adamw_skips_non_finite_gradients_and_recovers(cuda_lib):
+    """GradScaler semantics (timm NativeScaler, task_cruller_pretrain.py:259-268): a step with inf / nan gradients leaves
+    parameters and moments untouched, does NOT count as an update, still clears the gradients, and the next clean step
+    behaves exactly like torch.optim.AdamW's first step."""
+    from pixparse_b200 import ops
+    torch.manual_seed(12)
+    n = 64 * 1024
+    p = torch.randn(n, device=DEV)
+    p0 = p.clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    p16 = p.bfloat16()
+    segs = _segments([(n, 1.0, 0.0)])
+    stats = torch.zeros(4, device=DEV)
+    for bad in (float("inf"), float("nan")):
+        g = torch.randn(n, device=DEV) * 0.01
+        g[12345] = bad
+        ops.grad_norm(g, max_norm=1.0, out=stats)
+        ops.adamw_step(p, g, m, v, p16, segs, 1, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, norm_stats=stats)
+        assert torch.equal(p, p0) and m.abs().max().item() == 0.0 and v.abs().max().item() == 0.0
+        assert g.abs().max().item() == 0.0          # cleared: nothing non-finite survives into the next accumulation
+        assert stats[3].item() == 0.0               # not an applied update
+    g = torch.randn(n, device=DEV) * 0.01
+    pr = p0.clone().requires_grad_(True)
+    pr.grad = g.clone()
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.0)
+    torch.nn.utils.clip_grad_norm_([pr], 1.0)
+    opt.step()
+    ops.grad_norm(g, max_norm=1.0, out=stats)
+    ops.adamw_step(p, g, m, v, p16, segs, 1, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, norm_stats=stats)
+    assert stats[3].item() == 1.0
+    assert not torch.equal(p, p0)
+    assert (p - pr.detach()).abs().max().item() < 2e-6      # bias correction of step ONE, not three
+
+
+def test_wgrad_gemm_fused_bias_gradient(cuda_lib):
+    """dW = dY^T X with the nn.Linear bias gradient colsum(dY) summed from the staged A tiles (B200GemmArgs.bias_grad):
+    ragged token / feature counts, CTA pairs and single CTAs, split-K, accumulation onto existing values."""
+    from pixparse_b200 import ops
+    torch.manual_seed(13)
+    # (tokens, out features, in features): encoder fc1 / proj like shapes, ragged everything, tiny
+    for tokens, n_out, n_in in [(1009, 3072, 768), (2000, 768, 768), (515, 200, 264), (64, 16, 8), (4100, 1536, 768)]:
+        pad8 = lambda k: (k + 7) // 8 * 8
+        dy = torch.randn((tokens, pad8(n_out)), device=DEV).bfloat16()
+        x = torch.randn((tokens, pad8(n_in)), device=DEV).bfloat16()
+        dw = torch.zeros((n_out, n_in), device=DEV)
+        db = torch.full((n_out,), 0.5, device=DEV)
+        ops.gemm(dy, x, a_mn=True, b_mn=True, epi=ops.EPI_REDUCE_F32, out=dw, M=n_out, N=n_in, K=tokens, bias_grad=db)
+        ref_w = dy.float()[:, :n_out].t() @ x.float()[:, :n_in]
+        ref_b = dy.float()[:, :n_out].sum(0) + 0.5
+        assert rel_err(dw, ref_w) < 1e-5, (tokens, n_out, n_in)
+        assert (db - ref_b).abs().max().item() < 1e-3 * max(1.0, ref_b.abs().max().item()), (tokens, n_out, n_in)
 
 
 @pytest.mark.parametrize("Hin,Win,Hout,Wout", [(1100, 850, 576, 448), (330, 250, 576, 448), (64, 48, 64, 48),
