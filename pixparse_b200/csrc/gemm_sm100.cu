@@ -45,7 +45,7 @@ struct GemmParams {
   // STORE_BF16 / GELU_BF16: outputs leave through TMA stores (needs 16-byte aligned base and row pitch)
   int tma_epi;
   // REDUCE_F32 + A MN-major (weight gradients): bias_grad[m] += sum_k A(m, k), summed from the staged A tiles by the two
-  // otherwise idle control warps (10, 11) on the n_tile == 0 work items
+  // otherwise idle control warps (10, 11); the k-blocks are dealt round-robin to the n_tiles items that share an A panel
   float* bias_grad;
 };
 
@@ -434,8 +434,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // dW = dY^T X reduces over tokens; its A operand IS dY (MN-major: 64 tokens x 128 features per stage, two 64-feature
     // chunks of 128-byte rows, SWIZZLE_128B), so the nn.Linear bias gradient colsum(dY) is summed straight from the staged
     // tiles: warp 10 / 11 take one chunk each, lane l owns features 2l, 2l+1 (one conflict-free 128-byte row read per
-    // token). Only the n_tile == 0 work items contribute (every n_tile sees the same A). Every stage is waited for and
-    // released by these warps too, which keeps them in lock-step with the ring (an arrive can never run a phase ahead).
+    // token). The n_tiles work items of one (m_tile, split) all see the same A k-blocks: item n_tile sums the k-blocks with
+    // kb % n_tiles == n_tile, which spreads the extra shared-memory reads evenly over CTAs and k-blocks (summing everything
+    // on the n_tile == 0 items made those items ~30 % slower: the LDS queue behind the tensor core's operand fetches).
+    // Every stage is waited for and released by these warps too, which keeps them in lock-step with the ring (an arrive
+    // can never run a phase ahead).
     const int chunk = warp - 10;
     int stage = 0;
     uint32_t phase = 0;
@@ -443,10 +446,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int m_tile, n_tile, split;
       decode_work(p, w, m_tile, n_tile, split);
       if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
-      const bool mine = (n_tile == 0);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-      f32x2 acc0 = f2_splat(0.f), acc1 = f2_splat(0.f);
+      int turn = kb0 % p.n_tiles;       // k-block kb belongs to the item with n_tile == kb % n_tiles
+      // lane -> (row phase rq = lane / 8, 16-byte piece c16 = lane % 8): one LDS.128 covers four token rows of the
+      // chunk (512 bytes, conflict-free), 16 of them per k-block; each lane keeps 8 feature sums for its row phase
+      f32x2 acc[4] = {f2_splat(0.f), f2_splat(0.f), f2_splat(0.f), f2_splat(0.f)};
+      const int rq = lane >> 3, c16 = lane & 7;
       for (int kb = kb0; kb < kb1; ++kb) {
         if (CG == 2 && cta_rank != 0) {
           mbar_wait(&landed_bar[stage], phase);
@@ -455,15 +461,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           // all bytes of a pair's stage are credited to the leader's barrier: relay "landed" to the peer CTA
           if (CG == 2 && chunk == 0 && lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&landed_bar[stage]), 1));
         }
+        const bool mine = (turn == n_tile);
+        if (++turn == p.n_tiles) turn = 0;
         if (mine) {
-          const uint32_t base = smem_u32(smem + stage * Cfg::STAGE_BYTES) + chunk * (BK * 128) + (lane & 3) * 4;
-          const int c16 = lane >> 2;
-#pragma unroll 8
-          for (int r = 0; r < BK; r += 2) {
-            const uint32_t w0 = lds32(base + r * 128 + ((c16 ^ (r & 7)) << 4));
-            const uint32_t w1 = lds32(base + (r + 1) * 128 + ((c16 ^ ((r + 1) & 7)) << 4));
-            acc0 = f2_add(acc0, f2_pack(bf16_lo(w0), bf16_hi(w0)));
-            acc1 = f2_add(acc1, f2_pack(bf16_lo(w1), bf16_hi(w1)));
+          const uint32_t base = smem_u32(smem + stage * Cfg::STAGE_BYTES) + chunk * (BK * 128) + rq * 128;
+#pragma unroll
+          for (int r4 = 0; r4 < BK / 4; ++r4) {
+            // row = 4 r4 + rq; its swizzle phase (row & 7) = (4 (r4 & 1) + rq): compile-time per unrolled copy up to rq
+            const uint4 w = lds128(base + r4 * 512 + ((c16 ^ (((r4 & 1) << 2) | rq)) << 4));
+            acc[0] = f2_add(acc[0], f2_pack(bf16_lo(w.x), bf16_hi(w.x)));
+            acc[1] = f2_add(acc[1], f2_pack(bf16_lo(w.y), bf16_hi(w.y)));
+            acc[2] = f2_add(acc[2], f2_pack(bf16_lo(w.z), bf16_hi(w.z)));
+            acc[3] = f2_add(acc[3], f2_pack(bf16_lo(w.w), bf16_hi(w.w)));
           }
         }
         __syncwarp();
@@ -473,12 +482,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           phase ^= 1;
         }
       }
-      if (mine) {
-        float s0, s1;
-        f2_unpack(f2_add(acc0, acc1), s0, s1);
-        const int row = m_tile * BM + chunk * 64 + 2 * lane;
-        if (row < p.M) atomicAdd(p.bias_grad + row, s0);
-        if (row + 1 < p.M) atomicAdd(p.bias_grad + row + 1, s1);
+      {
+        float sums[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f2_unpack(acc[j], sums[2 * j], sums[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {      // fold the four row phases (lanes 8 apart)
+          sums[j] += __shfl_xor_sync(0xffffffffu, sums[j], 8);
+          sums[j] += __shfl_xor_sync(0xffffffffu, sums[j], 16);
+        }
+        if (rq == 0) {
+          const int row = m_tile * BM + chunk * 64 + c16 * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (row + j < p.M) atomicAdd(p.bias_grad + row + j, sums[j]);
+        }
       }
     }
   } else if (warp < 8) {
