@@ -36,7 +36,7 @@ BART_CONFIGS = {
     "facebook/bart-large": dict(
         vocab_size=50265, d_model=1024, encoder_layers=12, decoder_layers=12, encoder_attention_heads=16,
         decoder_attention_heads=16, encoder_ffn_dim=4096, decoder_ffn_dim=4096, activation_function="gelu",
-        dropout=0.1, attention_dropout=0.0, activation_dropout=0.0, max_position_embeddings=1024, init_std=0.02,
+        dropout=0.1, attention_dropout=0.1, activation_dropout=0.1, max_position_embeddings=1024, init_std=0.02,
         scale_embedding=False, pad_token_id=1, bos_token_id=0, eos_token_id=2, decoder_start_token_id=2),
     # tiny decoder for fast tests (same code path)
     "test/bart-tiny": dict(

@@ -88,14 +88,17 @@ VIT_ARCHS = {
                                   std=(0.26862954, 0.26130258, 0.27577711)),
 }
 
-# facebook/bart-* config.json constants
+# facebook/bart-* config.json constants. The hub is unreachable from here, so these are restated
+# from the public files: both bart-base and bart-large ship dropout = attention_dropout = activation_dropout = 0.1 (the
+# 0.0 / 0.0 attention / activation rates belong to the fine-tuned bart-large-cnn / -xsum / -mnli configs and to
+# BartConfig's own defaults). When the real config.json is in the local HF cache, `bart_arch()` takes its values instead.
 BART_ARCHS = {
     "facebook/bart-base": dict(vocab_size=50265, d_model=768, decoder_layers=6, decoder_attention_heads=12,
                                decoder_ffn_dim=3072, dropout=0.1, attention_dropout=0.1, activation_dropout=0.1,
                                max_position_embeddings=1024, init_std=0.02, pad_token_id=1, bos_token_id=0,
                                eos_token_id=2),
     "facebook/bart-large": dict(vocab_size=50265, d_model=1024, decoder_layers=12, decoder_attention_heads=16,
-                                decoder_ffn_dim=4096, dropout=0.1, attention_dropout=0.0, activation_dropout=0.0,
+                                decoder_ffn_dim=4096, dropout=0.1, attention_dropout=0.1, activation_dropout=0.1,
                                 max_position_embeddings=1024, init_std=0.02, pad_token_id=1, bos_token_id=0,
                                 eos_token_id=2),
     "test/bart-tiny": dict(vocab_size=50265, d_model=128, decoder_layers=2, decoder_attention_heads=2,
@@ -103,6 +106,27 @@ BART_ARCHS = {
                            max_position_embeddings=1024, init_std=0.02, pad_token_id=1, bos_token_id=0,
                            eos_token_id=2),
 }
+
+
+_BART_KEYS = ("vocab_size", "d_model", "decoder_layers", "decoder_attention_heads", "decoder_ffn_dim", "dropout",
+              "attention_dropout", "activation_dropout", "max_position_embeddings", "init_std", "pad_token_id",
+              "bos_token_id", "eos_token_id")
+
+
+def bart_arch(name):
+    """Architecture / dropout constants of a BART checkpoint name: the real config.json when transformers finds it in the
+    local cache (AutoConfig.from_pretrained, as text_decoder_hf.py:13 does -- never the network), else the restated table."""
+    arch = dict(BART_ARCHS[name]) if name in BART_ARCHS else None
+    if not name.startswith("test/"):
+        try:
+            from transformers import AutoConfig
+            hf = AutoConfig.from_pretrained(name, local_files_only=True)
+            arch = {k: getattr(hf, k) for k in _BART_KEYS}
+        except Exception:      # offline and not cached: keep the restated constants
+            pass
+    if arch is None:
+        raise ValueError(f"unsupported text decoder {name!r}; supported offline: {sorted(BART_ARCHS)}")
+    return arch
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -287,9 +311,7 @@ class BartForCausalLMB200(nn.Module):
 
     def __init__(self, name, num_decoder_layers=None, max_length=None):
         super().__init__()
-        if name not in BART_ARCHS:
-            raise ValueError(f"unsupported text decoder {name!r}; supported: {sorted(BART_ARCHS)}")
-        cfg = dict(BART_ARCHS[name])
+        cfg = bart_arch(name)
         if num_decoder_layers is not None:
             cfg['decoder_layers'] = num_decoder_layers
         if max_length is not None:

@@ -97,3 +97,73 @@ class SyntheticBartTokenizer:
 
     def batch_decode(self, batch, **kw):
         return [self.decode(x) for x in batch]
+
+
+class CharTokenizer:
+    """Deterministic character-level stand-in for a HF tokenizer's __call__ interface (offline tests of the annotation
+    preprocessors): special tokens registered with add_special_tokens map to single ids, every other character to
+    4 + ord(c) % 5000; supports max_length / padding='max_length' / truncation like the calls in data/preprocess.py."""
+
+    class _Out:
+        def __init__(self, ids):
+            self.input_ids = ids
+
+    def __init__(self):
+        self.pad_token_id, self.eos_token_id, self.bos_token_id = PAD_ID, EOS_ID, 0
+        self.pad_token, self.eos_token, self.bos_token = "<pad>", "</s>", "<s>"
+        self._special = {"<s>": 0, "<pad>": 1, "</s>": 2, "<unk>": 3}
+        self._next = 6000
+
+    def __len__(self):
+        return self._next
+
+    def add_special_tokens(self, d):
+        n = 0
+        for t in d.get("additional_special_tokens", []):
+            if t not in self._special:
+                self._special[t] = self._next
+                self._next += 1
+                n += 1
+        return n
+
+    def convert_tokens_to_ids(self, t):
+        return self._special.get(t, 3)
+
+    def _encode(self, text):
+        ids, i = [], 0
+        specials = sorted(self._special, key=len, reverse=True)
+        while i < len(text):
+            for s in specials:
+                if text.startswith(s, i):
+                    ids.append(self._special[s])
+                    i += len(s)
+                    break
+            else:
+                ids.append(4 + ord(text[i]) % 5000)
+                i += 1
+        return ids
+
+    def __call__(self, text, add_special_tokens=False, return_tensors='pt', max_length=None, padding=None,
+                 truncation=False):
+        ids = self._encode(text)
+        if truncation and max_length is not None:
+            ids = ids[:max_length]
+        if padding == 'max_length' and max_length is not None:
+            ids = ids + [self.pad_token_id] * (max_length - len(ids))
+        return CharTokenizer._Out(torch.tensor([ids], dtype=torch.int64))
+
+
+def synthetic_ocr_annotation(seed, max_pages=4):
+    """A pixparse OCR annotation: {'pages': [{'text': [line, ...]}, ...]} with some empty pages (data/preprocess.py:43)."""
+    import random
+    r = random.Random(seed)
+    pages = []
+    for _ in range(r.randint(1, max_pages)):
+        if r.random() < 0.3:
+            pages.append({"text": []})
+        else:
+            pages.append({"text": ["".join(r.choice("abcdefghij klmnop") for _ in range(r.randint(3, 30)))
+                                   for _ in range(r.randint(1, 5))]})
+    if not any(p["text"] for p in pages):
+        pages[r.randrange(len(pages))]["text"] = ["fallback line"]
+    return {"pages": pages}

@@ -97,8 +97,10 @@ class TaskCrullerPretrain(TaskTrain):
             {"additional_special_tokens": sorted(set(special_tokens))})
         self.vocab_size = len(self.tokenizer.trunk)
 
+        # text_anno_fn=False (pre-training on OCR annotations) selects the page-sampling OCR preprocessor, exactly as the
+        # reference wires it (task_cruller_pretrain.py:102-109)
         self.anno_preprocess_train = partial(
-            preprocess_text_tokens, tokenizer=self.tokenizer.trunk,
+            preprocess_text_tokens if self.text_anno_fn else preprocess_ocr_anno, tokenizer=self.tokenizer.trunk,
             max_position_embeddings=self.max_position_embeddings, task_start_token=self.task_start_token,
             prompt_end_token=self.prompt_end_token)
 
@@ -306,3 +308,63 @@ def preprocess_text_tokens(anno, tokenizer, max_position_embeddings, task_start_
     prompt_end_token_id = tokenizer.convert_tokens_to_ids(prompt_end_token)
     target[:torch.nonzero(target == prompt_end_token_id).sum() + 1] = ignore_id
     return dict(text=[ids], target=[target])
+
+
+def _tokenize_padded(tokenizer, text, max_len):
+    return tokenizer(text, add_special_tokens=False, return_tensors='pt', max_length=max_len, padding='max_length',
+                     truncation=True).input_ids[0]
+
+
+def _prompt_masked_target(ids, pad_id, prompt_end_id, ignore_id):
+    target = ids.clone()
+    target[target == pad_id] = ignore_id
+    target[:torch.nonzero(target == prompt_end_id).sum() + 1] = ignore_id
+    return target
+
+
+def next_page_with_text(index, num_pages, anno, retries=10):
+    """data/preprocess.py:112-131: the next page (cyclically) whose 'text' is non-empty, within `retries` tries."""
+    for _ in range(retries):
+        index = (index + 1) % num_pages
+        if anno['pages'][index]['text']:
+            return index
+    raise RuntimeError(f"No non-empty page found after {retries} attempts")
+
+
+def preprocess_ocr_anno(anno, tokenizer, max_position_embeddings, task_start_token, prompt_end_token, ignore_id=-100,
+                        generator=None):
+    """pixparse OCR annotation ``{'pages': [{'text': [line, ...], ...}, ...]}`` -> one randomly sampled page with text,
+    its lines joined by newlines, tokenised / padded / masked like the raw-text path (data/preprocess.py:43-110).
+    ``generator`` is a ``random.Random``-like object (``randint`` inclusive on both ends), as chug passes it.
+    Returns ``(dict(text=[ids], target=[ids]), dict(page_indices, num_pages, orig_text))``."""
+    if isinstance(anno, list):          # legacy [id, {...}] form
+        _logger.warning("Old [id, {}] annotation form found, correcting...")
+        anno = anno[1]
+    if not isinstance(anno, dict) or 'pages' not in anno:
+        raise TypeError("preprocess_ocr_anno expects a pixparse OCR annotation dict with a 'pages' list; raw-text "
+                        "annotations go through preprocess_text_tokens (task.text_anno_fn = True)")
+    num_pages = len(anno['pages'])
+    if not num_pages:
+        raise RuntimeError("Empty annotation. Skipping...")
+    if generator is None:
+        import random
+        generator = random
+    index = generator.randint(0, num_pages - 1)
+    if not anno['pages'][index]['text']:
+        index = next_page_with_text(index, num_pages, anno)
+    pad_id = tokenizer.pad_token_id
+    prompt_end_id = tokenizer.convert_tokens_to_ids(prompt_end_token)
+    texts, targets, indices = [], [], []
+    orig_text = None
+    wanted = min(1, num_pages)          # single-page mode, as in the reference
+    while len(texts) < wanted:
+        page = anno['pages'][index]
+        if not page['text']:
+            raise RuntimeError("No text on page, skipping...")
+        orig_text = '\n'.join(page['text'])
+        ids = _tokenize_padded(tokenizer, task_start_token + orig_text + tokenizer.eos_token, max_position_embeddings)
+        texts.append(ids)
+        targets.append(_prompt_masked_target(ids, pad_id, prompt_end_id, ignore_id))
+        indices.append(index)
+        index = next_page_with_text(index, num_pages, anno)
+    return dict(text=texts, target=targets), dict(page_indices=indices, num_pages=num_pages, orig_text=orig_text)

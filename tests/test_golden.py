@@ -93,3 +93,34 @@ def test_b200_train_steps_match_reference_golden(cuda_lib, name):
         assert opt.norm_stats[1].item() == pytest.approx(refstep["grad_norm"], rel=2e-2)
         lr = sum(pg["lr"] for pg in opt.param_groups) / len(opt.param_groups)
         assert lr == pytest.approx(refstep["lr_after"], rel=1e-9, abs=1e-15)
+
+
+def test_annotation_preprocessors_match_reference_golden():
+    """preprocess_ocr_anno (page sampling with the caller's generator, empty-page skipping, legacy list form) and the
+    raw-text preprocessor against vectors written by the reference's own functions (oracle/gen_golden_preprocess.py,
+    data/preprocess.py:9-110)."""
+    import random
+    from pixparse_b200 import synthetic
+    from pixparse_b200.task_pretrain import preprocess_ocr_anno, preprocess_text_tokens
+    g = _load("preprocess_anno")
+    n_ocr = 0
+    for case in g["cases"]:
+        tok = synthetic.CharTokenizer()
+        tok.add_special_tokens({"additional_special_tokens": sorted({"<sep/>", "<s_pretrain>"})})
+        if case["kind"] == "ocr":
+            anno = synthetic.synthetic_ocr_annotation(case["seed"])
+            if case["seed"] == 7:
+                anno = [17, anno]
+            out, info = preprocess_ocr_anno(anno, tok, g["max_len_ocr"], "<s_pretrain>", "<s_pretrain>",
+                                            generator=random.Random(100 + case["seed"]))
+            assert info == case["info"]
+            n_ocr += 1
+        else:
+            out = preprocess_text_tokens(case["raw"], tok, g["max_len_text"], "<s_pretrain>", "<s_pretrain>")
+        assert [t.tolist() for t in out["text"]] == case["text"]
+        assert [t.tolist() for t in out["target"]] == case["target"]
+    assert n_ocr == 12
+    with pytest.raises(TypeError):
+        preprocess_ocr_anno("raw text is not an OCR annotation", synthetic.CharTokenizer(), 16, "<s_pretrain>", "<s_pretrain>")
+    with pytest.raises(RuntimeError):
+        preprocess_ocr_anno({"pages": []}, synthetic.CharTokenizer(), 16, "<s_pretrain>", "<s_pretrain>")
