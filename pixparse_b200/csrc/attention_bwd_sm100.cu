@@ -10,6 +10,8 @@
 // exactly as TMA delivers them (K-major for S / dP, MN-major for dV / dK / dQ).
 //
 // Replaces the SDPA backward kernels autograd reaches from timm Attention and BartAttention.
+#include <type_traits>
+
 #include "attention_bwd_common.cuh"
 #include "../../include/pixparse_b200.h"
 
@@ -230,6 +232,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_drained);
+#pragma unroll
+      for (int e = 0; e < 64; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * p.scale);      // dQ = (dS / scale) K * scale
       if (dt == 0) tma_wait_group_read<0>();     // the previous reduce has finished reading the staging tiles
       named_bar_sync(1, 128);
 #pragma unroll
@@ -294,29 +298,47 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_wait(s_full, t & 1);
       AB_STAMP(1);
       tc_fence_after();
+      // (two instantiations: interior tiles -- all but the ragged last key tile and the causal diagonal -- carry no masking
+      //  instructions at all; as a runtime flag the mask cost every tile 64 ISETP + 64 FSEL, a fifth of this loop's
+      //  instructions, on warps that are issue / latency bound at two per scheduler)
+      auto stage_a = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t rs[32];
-        tmem_ld_32x32(lane_addr + TB_S + half * 64 + c * 32, rs);
-        tmem_ld_wait();
+        for (int c = 0; c < 2; ++c) {
+          uint32_t rs[32];
+          tmem_ld_32x32(lane_addr + TB_S + half * 64 + c * 32, rs);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float v0 = ex2_approx(fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2));
-          float v1 = ex2_approx(fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2));
-          if (need_mask) {
-            if (kbase + c * 32 + e > kmax) v0 = 0.f;
-            if (kbase + c * 32 + e + 1 > kmax) v1 = 0.f;
+          for (int e = 0; e < 32; e += 2) {
+            // All eight compute warps run this stage at the same time (they wait for the same S tile), two per scheduler:
+            // 2 x 64 MUFU.EX2 x 8 cycles = 1024 cycles of XU pipe per tile while the FMA pipe idles (ncu: this stage was
+            // 41 % of the compute warps' time). Every other element pair goes through the FMA-pipe polynomial instead.
+            const float a0 = fmaf(__uint_as_float(rs[e]), p.scale_log2, -lse2);
+            const float a1 = fmaf(__uint_as_float(rs[e + 1]), p.scale_log2, -lse2);
+            float v0, v1;
+            // (not under dropout: that variant is issue-bound on its mask hashing and sits at the 128-register limit)
+            if (!DROP && ((e >> 1) & 1)) {
+              ex2_poly2(a0, a1, v0, v1);
+            } else {
+              v0 = ex2_approx(a0);
+              v1 = ex2_approx(a1);
+            }
+            if (MASKED) {
+              if (kbase + c * 32 + e > kmax) v0 = 0.f;
+              if (kbase + c * 32 + e + 1 > kmax) v1 = 0.f;
+            }
+            uint32_t w = pack_bf16(v0, v1);
+            if (DROP) {
+              const uint32_t hsh = dropout_hash(p.drop_seed, drop_row + (uint32_t)((c * 32 + e) >> 1));
+              const bool keep0 = (hsh & 0xFFFFu) >= p.drop_threshold16, keep1 = (hsh >> 16) >= p.drop_threshold16;
+              pd[DROP ? c * 16 + (e >> 1) : 0] = pack_bf16(keep0 ? v0 * drop_sc : 0.f, keep1 ? v1 * drop_sc : 0.f);
+              w |= (keep0 ? 0u : 0x8000u) | (keep1 ? 0u : 0x80000000u);
+            }
+            pk[c * 16 + (e >> 1)] = w;
           }
-          uint32_t w = pack_bf16(v0, v1);
-          if (DROP) {
-            const uint32_t hsh = dropout_hash(p.drop_seed, drop_row + (uint32_t)((c * 32 + e) >> 1));
-            const bool keep0 = (hsh & 0xFFFFu) >= p.drop_threshold16, keep1 = (hsh >> 16) >= p.drop_threshold16;
-            pd[DROP ? c * 16 + (e >> 1) : 0] = pack_bf16(keep0 ? v0 * drop_sc : 0.f, keep1 ? v1 * drop_sc : 0.f);
-            w |= (keep0 ? 0u : 0x8000u) | (keep1 ? 0u : 0x80000000u);
-          }
-          pk[c * 16 + (e >> 1)] = w;
         }
-      }
+      };
+      if (need_mask) stage_a(std::true_type{}); else stage_a(std::false_type{});
       AB_STAMP(2);
       if (t > 0) mbar_wait(p_free, (t - 1) & 1);      // dV_{t-1} no longer reads the P buffer
       {
@@ -339,7 +361,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       AB_STAMP(7);
 
       // ---------------- stage B: dS_t ----------------
-      const f32x2 ndsum2 = f2_splat(-dsum), scale2 = f2_splat(p.scale);
+      // dS is produced WITHOUT the softmax scale: dQ = (dS K) * scale is scaled by the (mostly idle) drain warps and
+      // dK = (dS^T Q) * scale once in the epilogue -- 32 FMUL2 fewer per thread and tile here
+      const f32x2 ndsum2 = f2_splat(-dsum);
       AB_STAMP(4);
       mbar_wait(dp_full, t & 1);
       AB_STAMP(5);
@@ -353,15 +377,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           tmem_ld_wait();
           float dsv[32];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {      // dS = P * (mask * dP - D) * scale, on packed fp32 pairs
+          for (int e = 0; e < 32; e += 2) {      // dS / scale = P * (mask * dP - D), on packed fp32 pairs
             uint32_t w = pk[c * 16 + (e >> 1)];
             f32x2 g = f2_pack(__uint_as_float(rp[e]), __uint_as_float(rp[e + 1]));
             if (DROP) {
               g = f2_mul(g, f2_pack((w & 0x8000u) ? 0.f : drop_sc, (w & 0x80000000u) ? 0.f : drop_sc));
               w &= 0x7FFF7FFFu;
             }
-            const f32x2 ps = f2_mul(f2_pack(bf16_lo(w), bf16_hi(w)), scale2);
-            f2_unpack(f2_mul(f2_add(g, ndsum2), ps), dsv[e], dsv[e + 1]);
+            f2_unpack(f2_mul(f2_add(g, ndsum2), f2_pack(bf16_lo(w), bf16_hi(w))), dsv[e], dsv[e + 1]);
           }
           uint32_t dw[16];
 #pragma unroll
@@ -403,13 +426,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int e = 0; e < 32; ++e) r[e] = 0u;
       }
       if (k_ok) {
+        const float osc = which == 0 ? 1.0f : p.scale;      // dK accumulated dS^T Q without the softmax scale
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           uint4 o;
-          o.x = pack_bf16(__uint_as_float(r[8 * v4 + 0]), __uint_as_float(r[8 * v4 + 1]));
-          o.y = pack_bf16(__uint_as_float(r[8 * v4 + 2]), __uint_as_float(r[8 * v4 + 3]));
-          o.z = pack_bf16(__uint_as_float(r[8 * v4 + 4]), __uint_as_float(r[8 * v4 + 5]));
-          o.w = pack_bf16(__uint_as_float(r[8 * v4 + 6]), __uint_as_float(r[8 * v4 + 7]));
+          o.x = pack_bf16(__uint_as_float(r[8 * v4 + 0]) * osc, __uint_as_float(r[8 * v4 + 1]) * osc);
+          o.y = pack_bf16(__uint_as_float(r[8 * v4 + 2]) * osc, __uint_as_float(r[8 * v4 + 3]) * osc);
+          o.z = pack_bf16(__uint_as_float(r[8 * v4 + 4]) * osc, __uint_as_float(r[8 * v4 + 5]) * osc);
+          o.w = pack_bf16(__uint_as_float(r[8 * v4 + 6]) * osc, __uint_as_float(r[8 * v4 + 7]) * osc);
           *reinterpret_cast<uint4*>(orow + v4 * 8) = o;
         }
       }

@@ -464,6 +464,27 @@ __device__ __forceinline__ f32x2 gelu_erf_grad2(f32x2 x) {
   return f2_fma(f2_mul(x, f2_splat(0.3989422804014327f)), E, cdf);
 }
 
+// 2^x for x <= 0 on the FMA pipe, two values at a time (softmax probabilities; FA4-style MUFU offload). The attention
+// kernels are bound by the 16 ex2 / clk / SM of the XU pipe while their FMA pipe idles, so a share of the exponentials is
+// evaluated here instead: Cody-Waite reduction x = n + f with n = round(x) taken from the low mantissa bits of
+// x + 1.5 * 2^23, a degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, fifty times below
+// bf16 resolution -- every consumer rounds the result to bf16), and n added straight into the exponent field.
+// Arguments below -126 are clamped (2^-126 ~ 1e-38 stands in for 0; -inf marks padded rows).
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& y0, float& y1) {
+  const f32x2 x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const f32x2 t = f2_add(x, f2_splat(12582912.0f));                 // 1.5 * 2^23: ulp(t) = 1
+  const f32x2 n = f2_add(t, f2_splat(-12582912.0f));
+  const f32x2 f = f2_fma(n, f2_splat(-1.0f), x);
+  f32x2 p = f2_fma(f, f2_splat(5.517166853e-02f), f2_splat(2.426111251e-01f));
+  p = f2_fma(p, f, f2_splat(6.932609677e-01f));
+  p = f2_fma(p, f, f2_splat(9.999280572e-01f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
