@@ -54,6 +54,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* dq_drained = bars + 12;   // 128 arrivals (drain warps): dQ_t has left TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kv_tile = blockIdx.x;
@@ -100,6 +101,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == AB_TMA_WARP) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -450,6 +452,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 // lse2_pad = LSE * log2(e) (+inf beyond Sq -> P = 0 for padded queries), dsum_pad (0 beyond Sq).
 __global__ void attention_bwd_pad_kernel(float* __restrict__ lse2_pad, float* __restrict__ dsum_pad, int BH, int Sq,
                                          int Sq_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int npad = Sq_pad - Sq;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BH * npad; i += gridDim.x * blockDim.x) {
     const int bh = i / npad, q = Sq + i % npad;
@@ -461,6 +465,8 @@ __global__ void attention_bwd_prep_kernel(const bf16* __restrict__ o, long long 
                                           long long ld_do, int do_col0, float* __restrict__ dsum, int B, int H,
                                           int Sq, const float* __restrict__ lse, float* __restrict__ lse2_pad,
                                           float* __restrict__ dsum_pad, int Sq_pad, float* __restrict__ dq32) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)B * Sq * H * 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {      // total and the stride are multiples of 8: groups stay intact
@@ -496,6 +502,8 @@ __global__ void attention_bwd_prep_kernel(const bf16* __restrict__ o, long long 
 // dq bf16 [rows, ld_dq] (columns dq_col0 ..) = bf16(dq32 [rows, width])
 __global__ void attention_dq_convert_kernel(const float* __restrict__ dq32, bf16* __restrict__ dq, long long ld_dq,
                                             int dq_col0, long long rows, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int w4 = width / 4;
   const long long total = rows * w4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -567,12 +575,13 @@ extern "C" int b200_attention_bwd(const B200AttentionBwdArgs* a, void* stream) {
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
     if (Sq_pad > Sq) {
-      attention_bwd_pad_kernel<<<(B * H * (Sq_pad - Sq) + 255) / 256, 256, 0, s>>>(lse2_pad, dsum_pad, B * H, Sq, Sq_pad);
-      B200_CHECK_LAUNCH("attention_bwd_pad");
+      e = launch_kernel(attention_bwd_pad_kernel, dim3((B * H * (Sq_pad - Sq) + 255) / 256), dim3(256), 0, s, 1, lse2_pad,
+                        dsum_pad, B * H, Sq, Sq_pad);
+      if (e != cudaSuccess) return check_cuda(e, "attention_bwd_pad launch");
     }
-    attention_bwd_prep_kernel<<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const bf16*>(o), ld_o,
-                                                         reinterpret_cast<const bf16*>(d_o), ld_do, do_col0, dsum, B,
-                                                         H, Sq, lse, lse2_pad, dsum_pad, Sq_pad, dq32);
+    e = launch_kernel(attention_bwd_prep_kernel, dim3((unsigned)blocks), dim3(256), 0, s, 1, reinterpret_cast<const bf16*>(o), ld_o,
+                      reinterpret_cast<const bf16*>(d_o), ld_do, do_col0, dsum, B, H, Sq, lse, lse2_pad, dsum_pad, Sq_pad, dq32);
+    if (e != cudaSuccess) return check_cuda(e, "attention_bwd_prep launch");
     B200_CHECK_LAUNCH("attention_bwd_prep");
   }
 
@@ -615,9 +624,10 @@ extern "C" int b200_attention_bwd(const B200AttentionBwdArgs* a, void* stream) {
     configured = true;
   }
   dim3 grid((Sk + AB_T - 1) / AB_T, H, B);
-  if (p.drop_threshold16 != 0u) attention_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
-  else if (g_ab_query_major) attention_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, s>>>(tq, tk, tv, tdo, tdq, p);
+  if (p.drop_threshold16 != 0u) e = launch_kernel(attention_bwd_kernel<true>, grid, dim3(AB_THREADS), AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, p);
+  else if (g_ab_query_major) e = launch_kernel(attention_bwd_kernel<false>, grid, dim3(AB_THREADS), AB_SMEM, s, 1, tq, tk, tv, tdo, tdq, p);
   else if ((rc = launch_attention_bwd_kt(tq, tk, tv, tdo, tdq, p, pp, grid, s))) return rc;
+  if (e != cudaSuccess) return check_cuda(e, "attention_bwd launch");
   B200_CHECK_LAUNCH("attention_bwd");
 
   {
@@ -625,8 +635,9 @@ extern "C" int b200_attention_bwd(const B200AttentionBwdArgs* a, void* stream) {
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    attention_dq_convert_kernel<<<(int)blocks, 256, 0, s>>>(dq32, reinterpret_cast<bf16*>(dq), ld_dq, dq_col0,
-                                                           (long long)B * Sq, W);
+    e = launch_kernel(attention_dq_convert_kernel, dim3((unsigned)blocks), dim3(256), 0, s, 1, dq32, reinterpret_cast<bf16*>(dq),
+                      ld_dq, dq_col0, (long long)B * Sq, W);
+    if (e != cudaSuccess) return check_cuda(e, "attention_dq_convert launch");
     B200_CHECK_LAUNCH("attention_dq_convert");
   }
   return 0;

@@ -68,6 +68,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* o_full = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_tile = gridDim.x - 1 - blockIdx.x;   // heavy (late, causal) tiles first
@@ -107,6 +108,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 4) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
@@ -441,9 +443,11 @@ extern "C" int b200_attention_fwd(const B200AttentionFwdArgs* a, void* stream) {
     configured = true;
   }
   dim3 grid((Sq + ATT_BM - 1) / ATT_BM, H, B);
-  if (p.drop_threshold16 != 0u) attention_fwd_kernel<true, false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
-  else if (p.key_mask != nullptr) attention_fwd_kernel<false, true><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
-  else attention_fwd_kernel<false, false><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tq, tk, tv, p);
+  cudaError_t le;
+  if (p.drop_threshold16 != 0u) le = launch_kernel(attention_fwd_kernel<true, false>, grid, dim3(ATT_THREADS), ATT_SMEM, s, 1, tq, tk, tv, p);
+  else if (p.key_mask != nullptr) le = launch_kernel(attention_fwd_kernel<false, true>, grid, dim3(ATT_THREADS), ATT_SMEM, s, 1, tq, tk, tv, p);
+  else le = launch_kernel(attention_fwd_kernel<false, false>, grid, dim3(ATT_THREADS), ATT_SMEM, s, 1, tq, tk, tv, p);
+  if (le != cudaSuccess) return check_cuda(le, "attention_fwd launch");
   B200_CHECK_LAUNCH("attention_fwd");
   return 0;
 }

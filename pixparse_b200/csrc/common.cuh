@@ -44,6 +44,8 @@ int check_cuda(cudaError_t e, const char* what);
   } while (0)
 
 int num_sms();
+// Programmatic dependent launch (opt-in: PIXPARSE_B200_PDL=1): see launch_kernel() below
+bool pdl_enabled();
 
 // TMA descriptor encode (host). dims/strides innermost-first; strides in bytes for dims 1..rank-1.
 enum TmaSwizzle { TMA_SWIZZLE_NONE = 0, TMA_SWIZZLE_64B = 2, TMA_SWIZZLE_128B = 3 };
@@ -55,6 +57,16 @@ int make_tmap(CUtensorMap* out, const void* base, TmaDtype dt, int rank, const u
 // device helpers
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// ---- programmatic dependent launch --------------------------------------------------------------
+// The step is ~480 dependent kernels; launched back to back each one pays grid-launch latency plus its prologue
+// (barrier init, tensor-memory allocation, descriptor prefetch) AFTER its predecessor has drained. With the
+// programmatic-stream-serialization launch attribute a kernel's CTAs may become resident as soon as every CTA of the
+// predecessor has called pdl_launch_dependents() (first thing in every kernel here) and an SM has room, run their
+// prologue, and block in pdl_wait() until the predecessor grid has completed and its writes are visible. Rule: no
+// global-memory access of any kind before pdl_wait(). Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -524,6 +536,36 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Launch `kern` on `s` (optionally as clusters of cluster_x CTAs) with programmatic dependent launch when enabled.
+// Only kernels that follow the pdl_wait() rule above may go through here.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 #endif  // __CUDACC__

@@ -264,6 +264,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const bool biasg = CAN_BIASG && p.bias_grad != nullptr;
   float* epi_bias = reinterpret_cast<float*>(epi_buf + 2 * Cfg::EPI_GROUP_BYTES + 256);   // 2 groups x 128 floats
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // CTA pairs: rank inside the pair (0 = leader, issues the MMAs), work items are distributed over pairs
@@ -307,6 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue done; operands / outputs of the predecessor kernel are touched only from here on
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
 
@@ -782,25 +784,8 @@ static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
   }
-  if (CG == 2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = SMEM;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, p);
-    if (e != cudaSuccess) return check_cuda(e, "gemm_kernel (CTA pair) launch");
-  } else {
-    kern<<<grid, GEMM_THREADS, SMEM, stream>>>(ta, tb, to, to2, p);
-  }
+  cudaError_t e = launch_kernel(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), SMEM, stream, CG, ta, tb, to, to2, p);
+  if (e != cudaSuccess) return check_cuda(e, "gemm_kernel launch");
   B200_CHECK_LAUNCH("gemm_kernel launch");
   return 0;
 }

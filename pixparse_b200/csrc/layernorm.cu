@@ -17,6 +17,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
                      bf16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int rows, float eps, uint32_t drop_thr, uint32_t drop_seed) {
   constexpr int D = NV * 128;
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -75,6 +77,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy16, const float* __restrict__ dy
                      uint32_t in_thr, uint32_t in_seed, uint32_t out_thr, uint32_t out_seed) {
   constexpr int D = NV * 128;
   __shared__ float red[LN_WARPS][D];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float4 dg[NV], db[NV];
@@ -165,7 +169,9 @@ template <int NV>
 static int ln_fwd_launch(const float* x, const float* gamma, const float* beta, bf16* y16, float* y32, float* mean,
                          float* rstd, int rows, float eps, uint32_t thr, uint32_t seed, cudaStream_t s) {
   const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
-  layernorm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y16, y32, mean, rstd, rows, eps, thr, seed);
+  cudaError_t e = launch_kernel(layernorm_fwd_kernel<NV>, dim3(grid), dim3(LN_WARPS * 32), 0, s, 1, x, gamma, beta, y16, y32,
+                                mean, rstd, rows, eps, thr, seed);
+  if (e != cudaSuccess) return check_cuda(e, "layernorm_fwd launch");
   B200_CHECK_LAUNCH("layernorm_fwd");
   return 0;
 }
@@ -189,13 +195,14 @@ static int ln_bwd_launch(const bf16* dy16, const float* dy32, const float* dres3
   int grid = num_sms() * per_sm[drop];
   const int need = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > need) grid = need;
+  cudaError_t le;
   if (in_thr != 0u || out_thr != 0u)
-    layernorm_bwd_kernel<NV, true><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy32, dres32, x, mean, rstd, gamma, dx32, dx16,
-                                                                  dgamma, dbeta, rows, in_thr, in_seed, out_thr,
-                                                                  out_seed);
+    le = launch_kernel(layernorm_bwd_kernel<NV, true>, dim3(grid), dim3(LN_WARPS * 32), 0, s, 1, dy16, dy32, dres32, x, mean,
+                       rstd, gamma, dx32, dx16, dgamma, dbeta, rows, in_thr, in_seed, out_thr, out_seed);
   else      // the common (encoder) case carries no dropout code at all
-    layernorm_bwd_kernel<NV, false><<<grid, LN_WARPS * 32, 0, s>>>(dy16, dy32, dres32, x, mean, rstd, gamma, dx32, dx16,
-                                                                   dgamma, dbeta, rows, 0u, 0u, 0u, 0u);
+    le = launch_kernel(layernorm_bwd_kernel<NV, false>, dim3(grid), dim3(LN_WARPS * 32), 0, s, 1, dy16, dy32, dres32, x, mean,
+                       rstd, gamma, dx32, dx16, dgamma, dbeta, rows, 0u, 0u, 0u, 0u);
+  if (le != cudaSuccess) return check_cuda(le, "layernorm_bwd launch");
   B200_CHECK_LAUNCH("layernorm_bwd");
   return 0;
 }
