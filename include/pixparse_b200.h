@@ -280,6 +280,80 @@ typedef struct B200AdamWArgs {
 } B200AdamWArgs;
 int b200_adamw_step(const B200AdamWArgs* args, void* stream);
 
+/* ---- single-token greedy decode (BASELINE configs[4]) -----------------------------------
+ * One decode step feeds one new token per page: every linear has M = pages <= 16 rows and is bound by streaming its
+ * weights once. Per-step quantities (the position, the generated ids) are read from DEVICE memory, so a whole step is a
+ * fixed kernel sequence with fixed arguments that the host captures once in a CUDA graph and replays per token.
+ * Replaces the uncached loop of utils/ocr_utils.py:165-197 / the past_key_values branch of
+ * models/text_decoder_hf.py:69-70 for batch <= 16.
+ *
+ * decode_linear: y[M, N] = x[M, K] W[N, K]^T (+ bias) (act = 1: GELU on the bf16-rounded pre-activation) (+ fp32 resid);
+ *   outputs bf16 and/or fp32 with row pitch ldo, shifted by (*pos) * out_pos_stride elements when pos != NULL (appending
+ *   K | V to a [B, T_max, 2D] cache). With argmax_partial != NULL nothing is stored: the per-CTA (max, argmax) of the
+ *   bf16-rounded outputs is written as [b200_decode_linear_ctas(N)][16] packed 64-bit keys (LM head fused with argmax).
+ * decode_attention: one query per (page, head): q [B, ldq], K / V rows ld_kv apart, pages kv_bstride apart; the key
+ *   count is sk, or (*pos) + 1 when pos != NULL; key j of page b is hidden when key_ids[b * ld_ids + j] == pad_id
+ *   (attention_mask = input_ids.ne(pad), models/text_decoder_hf.py:68).
+ * decode_embed: x[b] = tok_emb[ids[b * ld_ids + *pos]] * scale + pos_emb[*pos + pos_offset]   (BartDecoder embedding).
+ * decode_finalize: token[b] = argmax over the partial keys (first index on ties); ids[b * ld_ids + *pos + 1] = token;
+ *   finished[b] |= token == eos; state = {pos, done_step, steps}: done_step (-1 until set) = first step at which every
+ *   page had emitted EOS -- the reference loop breaks there without appending; pos += 1.
+ */
+typedef struct B200DecodeLinearArgs {
+  unsigned int struct_size;
+  int m;
+  const void* x;
+  long long ldx;
+  const void* w;
+  long long ldw;
+  const float* bias;
+  const float* resid;
+  long long ld_resid;
+  void* out_bf16;
+  float* out_f32;
+  long long ldo;
+  const int* pos;
+  long long out_pos_stride;
+  void* argmax_partial;
+  int n;
+  int k;
+  int act;
+  int reserved;
+} B200DecodeLinearArgs;
+int b200_decode_linear(const B200DecodeLinearArgs* args, void* stream);
+int b200_decode_linear_ctas(int n);
+
+typedef struct B200DecodeAttentionArgs {
+  unsigned int struct_size;
+  int batch;
+  const void* q;
+  long long ldq;
+  const void* k;
+  const void* v;
+  long long ld_kv;
+  long long kv_bstride;
+  void* out;
+  long long ld_out;
+  const int* pos;
+  const long long* key_ids;
+  long long ld_ids;
+  long long pad_id;
+  int q_col0;
+  int k_col0;
+  int v_col0;
+  int heads;
+  int head_dim;
+  int sk;
+  float scale;
+  int reserved;
+} B200DecodeAttentionArgs;
+int b200_decode_attention(const B200DecodeAttentionArgs* args, void* stream);
+
+int b200_decode_embed(const long long* ids, long long ld_ids, const int* pos, const float* tok_emb, const float* pos_emb,
+                      float* x, int B, int D, int pos_offset, float scale, void* stream);
+int b200_decode_finalize(const void* argmax_partial, int n_cta, long long* ids, long long ld_ids, int* state,
+                         int* finished, int B, long long eos_id, void* stream);
+
 /* ---- on-device page preprocessing ------------------------------------------------------
  * uint8 'L' pages [B, Hin, Win] (page_stride bytes apart) -> fp32 [B, 1, Hout, Wout]:
  * ToTensor -> Resize(BICUBIC, antialias=True) -> Normalize(mean, std), i.e. the transforms.Compose built in

@@ -107,9 +107,23 @@ class AdamWArgs(_Args):
                 ("zero_grad", _I), ("reserved", _I)]
 
 
+class DecodeLinearArgs(_Args):
+    _fields_ = [("struct_size", _U), ("m", _I), ("x", _P), ("ldx", _L), ("w", _P), ("ldw", _L), ("bias", _P), ("resid", _P),
+                ("ld_resid", _L), ("out_bf16", _P), ("out_f32", _P), ("ldo", _L), ("pos", _P), ("out_pos_stride", _L),
+                ("argmax_partial", _P), ("n", _I), ("k", _I), ("act", _I), ("reserved", _I)]
+
+
+class DecodeAttentionArgs(_Args):
+    _fields_ = [("struct_size", _U), ("batch", _I), ("q", _P), ("ldq", _L), ("k", _P), ("v", _P), ("ld_kv", _L),
+                ("kv_bstride", _L), ("out", _P), ("ld_out", _L), ("pos", _P), ("key_ids", _P), ("ld_ids", _L),
+                ("pad_id", _L), ("q_col0", _I), ("k_col0", _I), ("v_col0", _I), ("heads", _I), ("head_dim", _I),
+                ("sk", _I), ("scale", _F), ("reserved", _I)]
+
+
 # C struct name (header) -> ctypes mirror
 STRUCTS = {"B200GemmArgs": GemmArgs, "B200AttentionFwdArgs": AttentionFwdArgs, "B200AttentionBwdArgs": AttentionBwdArgs,
-           "B200LayerNormFwdArgs": LayerNormFwdArgs, "B200LayerNormBwdArgs": LayerNormBwdArgs, "B200AdamWArgs": AdamWArgs}
+           "B200LayerNormFwdArgs": LayerNormFwdArgs, "B200LayerNormBwdArgs": LayerNormBwdArgs, "B200AdamWArgs": AdamWArgs,
+           "B200DecodeLinearArgs": DecodeLinearArgs, "B200DecodeAttentionArgs": DecodeAttentionArgs}
 
 # name -> argtypes; mirrors include/pixparse_b200.h (tests/test_abi.py compares every prototype and struct field)
 SIGNATURES = {
@@ -136,6 +150,11 @@ SIGNATURES = {
     "b200_grad_norm": [_P, _L, _P, _P, _F, _F, _P],
     "b200_grad_norm_workspace_floats": [],
     "b200_preprocess_pages": [_P, _I, _I, _I, _L, _P, _I, _I, _F, _F, _P, _P],
+    "b200_decode_linear": [ctypes.POINTER(DecodeLinearArgs), _P],
+    "b200_decode_linear_ctas": [_I],
+    "b200_decode_attention": [ctypes.POINTER(DecodeAttentionArgs), _P],
+    "b200_decode_embed": [_P, _L, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "b200_decode_finalize": [_P, _I, _P, _L, _P, _P, _I, _L, _P],
 }
 # entry points whose return type is not int
 RESTYPES = {"b200_last_error": ctypes.c_char_p, "b200_attention_bwd_workspace_bytes": ctypes.c_longlong,
@@ -189,6 +208,13 @@ def reset_launch_count():
 
 def launch_count():
     return _launches
+
+
+def add_launches(n):
+    """Kernel launches that did not go through call(): replays of a captured CUDA graph (n = kernel nodes x replays;
+    negative to take back the launches counted while capturing)."""
+    global _launches
+    _launches += int(n)
 
 
 def call(name, *args):

@@ -146,10 +146,12 @@ class CrullerEngine:
         # seed + rank, so DDP ranks draw different masks) the first time a training forward needs it.
         self.dropout_seed = None
         self._dropout_calls = 0
+        self._decode_sessions = {}
 
     # ------------------------------------------------------------------------------------------------ binding
     def invalidate(self):
         self.arena = None
+        self._decode_sessions = {}
 
     def _ordered_params(self):
         """Physical arena order: q|k|v (and cross k|v) weights adjacent so they act as one packed GEMM operand."""
@@ -660,6 +662,24 @@ class CrullerEngine:
         V = self.arena.index["dec.tok"][2][0]
         logits = logits.view(B, input_ids.shape[1], -1)[:, :, :V]
         return (logits, cache) if (use_cache or past_key_values is not None) else logits
+
+    def greedy_decode(self, encoder_hidden_states, prompt_id, max_new_tokens, eos_id, pad_id, stop_on_eos=True):
+        """The greedy loop of utils/ocr_utils.py:165-197 for up to 16 pages as a replayed CUDA graph of single-token
+        kernels (pixparse_b200/decode.py). Returns ids [B, 1 + n]."""
+        from .decode import MAX_PAGES, GreedyDecodeSession
+        self.refresh_shadow()
+        B, S, D = encoder_hidden_states.shape
+        assert B <= MAX_PAGES, f"graph decode handles at most {MAX_PAGES} pages per call"
+        enc16 = encoder_hidden_states.reshape(B * S, D)
+        if enc16.dtype != torch.bfloat16:
+            enc16 = enc16.to(torch.bfloat16)
+        enc16 = enc16.contiguous()
+        key = (B, S, id(self.arena))
+        sess = self._decode_sessions.get(key)
+        if sess is None:
+            self._decode_sessions.clear()      # one live session: its caches are sized for max_position_embeddings
+            sess = self._decode_sessions[key] = GreedyDecodeSession(self, B, S)
+        return sess.run(enc16, prompt_id, max_new_tokens, eos_id, pad_id, stop_on_eos=stop_on_eos)
 
     def forward_logits(self, image, text_ids):
         """Cruller.forward. Under autograd the returned logits carry a backward that runs the fused kernels."""

@@ -51,14 +51,21 @@ def get_next_token(next_token_logits, use_sample: bool = True, temperature: floa
 
 
 def get_generated_tokens(model, tokenizer, encoder_outputs, device_env, max_recursion_length, prompt_token: str,
-                         use_cache: bool = False, stop_on_eos: bool = True):
+                         use_cache: bool = False, stop_on_eos: bool = True, graph_decode: bool = True):
     """use_cache=False is the reference loop (whole prefix re-fed each step). use_cache=True feeds only the last token
     and carries ``past_key_values`` (the branch prepare_inputs_for_inference already has, text_decoder_hf.py:69-70):
-    same token ids, O(steps) instead of O(steps^2) decoder work.
+    same token ids, O(steps) instead of O(steps^2) decoder work; with graph_decode (default, <= 16 pages) the cached loop
+    runs as one replayed CUDA graph per token, otherwise through TextDecoderHf.forward(past_key_values=...).
     stop_on_eos=False (benchmarks with random weights) always runs max_recursion_length steps and never reads the
     "all rows finished" flag back to the host."""
     task_prompt_id = tokenizer.trunk.encode(prompt_token, add_special_tokens=False)[0]
     device = device_env.device
+    if use_cache and graph_decode and encoder_outputs.shape[0] <= 16:
+        # up to 16 pages: the whole loop below as a replayed CUDA graph of single-token kernels (pixparse_b200/decode.py)
+        from .engine import engine_for
+        return engine_for(model.text_decoder).greedy_decode(
+            encoder_outputs, task_prompt_id, max_recursion_length, tokenizer.trunk.eos_token_id,
+            tokenizer.trunk.pad_token_id, stop_on_eos=stop_on_eos)
     input_ids = torch.full((encoder_outputs.shape[0], 1), task_prompt_id, dtype=torch.long, device=device)
     finished = torch.zeros(input_ids.shape[0], dtype=torch.bool, device=device)
     eos_token_id = tokenizer.trunk.eos_token_id

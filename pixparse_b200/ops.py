@@ -109,13 +109,17 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, *, B, H, Sq, Sk, q_col0=0, k
     return dq, dk, dv
 
 
-def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False, drop=None):
+def layernorm_fwd(x, gamma, beta, eps, *, want_bf16=True, want_f32=False, drop=None, out=None):
+    """out = (y16, y32, mean, rstd) preallocated (entries may be None): nothing is allocated (CUDA-graph capture)."""
     rows, dim = x.shape
     assert x.dtype == F32 and x.is_contiguous()
-    y16 = torch.empty((rows, dim), device=x.device, dtype=BF16) if want_bf16 else None
-    y32 = torch.empty((rows, dim), device=x.device, dtype=F32) if want_f32 else None
-    mean = torch.empty((rows,), device=x.device, dtype=F32)
-    rstd = torch.empty((rows,), device=x.device, dtype=F32)
+    if out is not None:
+        y16, y32, mean, rstd = out
+    else:
+        y16 = torch.empty((rows, dim), device=x.device, dtype=BF16) if want_bf16 else None
+        y32 = torch.empty((rows, dim), device=x.device, dtype=F32) if want_f32 else None
+        mean = torch.empty((rows,), device=x.device, dtype=F32)
+        rstd = torch.empty((rows,), device=x.device, dtype=F32)
     p, seed = drop if (drop is not None and drop[0] > 0.0) else (0.0, 0)
     args = _lib.LayerNormFwdArgs(rows=rows, x=ptr(x), gamma=ptr(gamma), beta=ptr(beta), y_bf16=ptr(y16), y_f32=ptr(y32),
                                  mean=ptr(mean), rstd=ptr(rstd), dim=dim, eps=float(eps), drop_p=float(p),
@@ -237,6 +241,58 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, params_bf16, segments, num_se
                           beta1=float(beta1), beta2=float(beta2), eps=float(eps), step=int(step),
                           zero_grad=int(zero_grad))
     call("b200_adamw_step", args, stream())
+
+
+# ---- single-token greedy decode (csrc/decode.cu) --------------------------------------------------------------------
+def decode_linear_ctas(n):
+    return _lib.lib().b200_decode_linear_ctas(int(n))
+
+
+def decode_linear(x, w, *, M, out16=None, out32=None, bias=None, resid=None, act=0, pos=None, out_pos_stride=0,
+                  argmax_partial=None, ldo=None):
+    """y[M, N] = x[M, K] w[N, K]^T (+ bias) (act=1: GELU) (+ resid fp32), M <= 16. Outputs bf16 (out16) and / or fp32 (out32)
+    with row pitch ldo (default: their stride(0)), shifted by pos[0] * out_pos_stride elements when pos (device int32) is
+    given. argmax_partial: nothing is stored, the per-CTA (max, argmax) keys of the bf16-rounded outputs are."""
+    assert x.dtype == BF16 and w.dtype == BF16 and x.dim() == 2 and w.dim() == 2
+    N, K = w.shape
+    assert x.shape[1] == K and x.shape[0] >= M
+    if ldo is None:
+        ref = out16 if out16 is not None else out32
+        ldo = ref.stride(0) if ref is not None else 0
+    args = _lib.DecodeLinearArgs(m=M, x=ptr(x), ldx=_ld(x), w=ptr(w), ldw=_ld(w), bias=ptr(bias), resid=ptr(resid),
+                                 ld_resid=_ld(resid) if resid is not None else 0, out_bf16=ptr(out16), out_f32=ptr(out32),
+                                 ldo=ldo, pos=ptr(pos), out_pos_stride=out_pos_stride, argmax_partial=ptr(argmax_partial),
+                                 n=N, k=K, act=act)
+    call("b200_decode_linear", args, stream())
+
+
+def decode_attention(q, k, v, out, *, B, H, ld_kv, kv_bstride, q_col0=0, k_col0=0, v_col0=0, sk=0, pos=None,
+                     key_ids=None, pad_id=0, scale=None):
+    """One query per (page, head) against K / V rows `ld_kv` elements apart (pages `kv_bstride` apart). Keys: sk, or
+    pos[0] + 1 when pos (device int32) is given; keys whose id in key_ids [B, ld] equals pad_id are hidden."""
+    if scale is None:
+        scale = 64 ** -0.5
+    args = _lib.DecodeAttentionArgs(batch=B, q=ptr(q), ldq=_ld(q), k=ptr(k), v=ptr(v), ld_kv=ld_kv, kv_bstride=kv_bstride,
+                                    out=ptr(out), ld_out=_ld(out), pos=ptr(pos), key_ids=ptr(key_ids),
+                                    ld_ids=key_ids.stride(0) if key_ids is not None else 0, pad_id=int(pad_id),
+                                    q_col0=q_col0, k_col0=k_col0, v_col0=v_col0, heads=H, head_dim=64, sk=int(sk),
+                                    scale=float(scale))
+    call("b200_decode_attention", args, stream())
+
+
+def decode_embed(ids, pos, tok_emb, pos_emb, x, pos_offset=2, scale=1.0):
+    B, D = x.shape
+    assert ids.dtype == torch.int64 and pos.dtype == torch.int32
+    call("b200_decode_embed", ptr(ids), ids.stride(0), ptr(pos), ptr(tok_emb), ptr(pos_emb), ptr(x), B, D, pos_offset,
+         float(scale), stream())
+
+
+def decode_finalize(partial, n_cta, ids, state, finished, eos_id):
+    """One token per row of ids [B, >= pos + 2]: argmax over the partial keys -> ids[:, pos + 1]; finished[:B] |= == eos."""
+    assert state.dtype == torch.int32 and finished.dtype == torch.int32 and ids.dtype == torch.int64
+    assert finished.numel() >= ids.shape[0]
+    call("b200_decode_finalize", ptr(partial), int(n_cta), ptr(ids), ids.stride(0), ptr(state), ptr(finished),
+         ids.shape[0], int(eos_id), stream())
 
 
 def release_workspaces():

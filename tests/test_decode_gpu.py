@@ -47,11 +47,12 @@ def _oracle_gap(ref, enc_ref_row, prefix):
     return top[0].item(), (top[0] - top[1]).item(), last.abs().max().item()
 
 
-@pytest.mark.parametrize("use_cache", [False, True])
-def test_large_6layers_greedy_decode_matches_oracle_loop(large6, use_cache):
+@pytest.mark.parametrize("mode", ["uncached", "cached_forward", "cached_graph"])
+def test_large_6layers_greedy_decode_matches_oracle_loop(large6, mode):
     """B = 16, 20 new tokens. Every row must reproduce the oracle's ids exactly up to the first step where the ORACLE's
     own top-1 / top-2 gap is inside bf16 noise (<= 3 % of max |logit|); a divergence anywhere else fails. The first
-    divergence step and its gap are reported."""
+    divergence step and its gap are reported. Modes: the reference's uncached loop on this repo's kernels; the
+    past_key_values branch through TextDecoderHf.forward; the single-token kernels replayed as a CUDA graph (decode.py)."""
     from oracle import cruller_ref
     from pixparse_b200 import synthetic
     from pixparse_b200.ocr_utils import get_generated_tokens
@@ -60,7 +61,7 @@ def test_large_6layers_greedy_decode_matches_oracle_loop(large6, use_cache):
     ids_ref = cruller_ref.greedy_decode_uncached(ref, enc_ref, synthetic.S_PRETRAIN_ID, 1, 2, steps)
     with torch.inference_mode():
         ids = get_generated_tokens(task.model, task.tokenizer, enc, task.device_env, steps, "<s_pretrain>",
-                                   use_cache=use_cache)
+                                   use_cache=mode != "uncached", graph_decode=mode == "cached_graph")
     n = min(ids.shape[1], ids_ref.shape[1])
     assert n >= 2 and (ids[:, 0] == synthetic.S_PRETRAIN_ID).all()
     exact_rows, report = 0, []
@@ -74,7 +75,7 @@ def test_large_6layers_greedy_decode_matches_oracle_loop(large6, use_cache):
         report.append((b, t, gap, mx))
         assert gap <= 0.03 * mx, (f"row {b} diverges from the oracle at step {t} although the oracle's top-1/top-2 gap "
                                   f"{gap:.4f} is far outside bf16 noise (max |logit| {mx:.2f})")
-    print(f"use_cache={use_cache}: {exact_rows}/16 rows identical to the oracle over {n - 1} tokens; "
+    print(f"{mode}: {exact_rows}/16 rows identical to the oracle over {n - 1} tokens; "
           f"first divergences (row, step, oracle gap, max|logit|): {report}")
     assert exact_rows >= 8      # the bulk of the rows must be exact, near-ties are the exception
 
@@ -110,3 +111,36 @@ def test_decoder_attention_mask_hides_pad_keys(large6):
     assert rel(got[:, 3:], want[:, 3:]) < 0.5 * rel(got[:, 3:], nomask[:, 3:])
     assert rel(out6.logits.float()[:, -1], want[:, -1]) < 1e-2
     assert rel(out5.logits.float(), want[:, :5]) < 1e-2
+
+
+def test_graph_decode_stops_like_the_reference_loop_and_masks_pad_keys(large6):
+    """The graph session against the step-by-step cached path of the same model (same weights, both bf16):
+    (a) EOS handling: with the token page 0 emits at step 5 declared EOS, a one-page run ends exactly where the reference
+    loop breaks -- the all-finished step is not appended (ocr_utils.py:192-195) -- and a 16-page run agrees with the
+    step-by-step path; (b) with the token emitted at step 2 declared PAD, later self-attention queries must not see that
+    key: the session (which reads the mask from its own ids) agrees with TextDecoderHf.forward(attention_mask=...)."""
+    from pixparse_b200.ocr_utils import get_generated_tokens
+    task, ref, enc, enc_ref = large6
+    tok = task.tokenizer.trunk
+    gen = lambda e, graph, **kw: get_generated_tokens(task.model, task.tokenizer, e, task.device_env, 12, "<s_pretrain>",
+                                                      use_cache=True, graph_decode=graph, **kw)
+    eos0, pad0 = tok.eos_token_id, tok.pad_token_id
+    with torch.inference_mode():
+        a = gen(enc, False, stop_on_eos=False)
+        assert a.shape == (16, 13)
+        try:
+            tok.eos_token_id = int(a[0, 6])
+            one = gen(enc[:1], True)
+            want, got = gen(enc, False), gen(enc, True)
+        finally:
+            tok.eos_token_id = eos0
+        first = (a[0, 1:] == int(a[0, 6])).nonzero()[0].item() + 1
+        assert one.shape[1] == first and (one[0] == a[0, :first]).all()
+        assert got.shape == want.shape and (got == want).float().mean().item() > 0.9      # only near-ties may differ
+        try:
+            tok.pad_token_id = int(a[0, 3])
+            want, got = gen(enc, False, stop_on_eos=False), gen(enc, True, stop_on_eos=False)
+        finally:
+            tok.pad_token_id = pad0
+        assert (got == want).float().mean().item() > 0.9
+        assert (got[0] == want[0]).all() or (want[0] != a[0]).any()

@@ -458,3 +458,87 @@ def test_page_preprocess_matches_torchvision(cuda_lib, Hin, Win, Hout, Wout):
     out = ops.preprocess_pages(pages.cuda(), (Hout, Wout), mean, std)
     assert out.shape == ref.shape
     assert (out.cpu() - ref).abs().max().item() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------- single-token decode
+@pytest.mark.parametrize("M,N,K", [(16, 1024, 1024), (5, 4096, 1024), (16, 1000, 4096), (1, 50267, 768), (16, 50286, 1024)])
+def test_decode_linear(cuda_lib, M, N, K):
+    """y = x W^T (+ bias, GELU, fp32 residual) for <= 16 rows against fp32 matmul; the LM-head mode returns the argmax of
+    the bf16-rounded logits (first index on ties) without storing them."""
+    from pixparse_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn((16, K), device=DEV).bfloat16()
+    w = (torch.randn((N, K), device=DEV) * K ** -0.5).bfloat16()
+    bias = torch.randn((N,), device=DEV)
+    resid = torch.randn((16, N), device=DEV)
+    ref = x[:M].float() @ w.float().t()
+    out32 = torch.full((16, N), 7.0, device=DEV)
+    ops.decode_linear(x, w, M=M, out32=out32, bias=bias, resid=resid)
+    assert rel_err(out32[:M], ref + bias + resid[:M]) < 1e-5
+    assert (out32[M:] == 7.0).all()
+    out16 = torch.zeros((16, N), device=DEV, dtype=torch.bfloat16)
+    ops.decode_linear(x, w, M=M, out16=out16, bias=bias, act=1)
+    want = F.gelu((ref + bias).bfloat16().float())
+    assert rel_err(out16[:M], want) < 4e-3
+    # fused argmax (LM head): partial keys -> finalize appends the token at ids[:, pos + 1]
+    n_cta = ops.decode_linear_ctas(N)
+    partial = torch.zeros((n_cta, 16), device=DEV, dtype=torch.int64)
+    ops.decode_linear(x, w, M=M, argmax_partial=partial)
+    ids = torch.zeros((M, 8), device=DEV, dtype=torch.int64)
+    state = torch.tensor([2, -1, 0, 0], device=DEV, dtype=torch.int32)
+    fin = torch.zeros(16, device=DEV, dtype=torch.int32)
+    logits16 = ref.bfloat16().float()
+    want_tok = logits16.argmax(1)
+    ops.decode_finalize(partial, n_cta, ids, state, fin, eos_id=int(want_tok[0]))
+    got_tok = ids[:, 3]
+    # the kernel's fp32 sums differ from torch's in the last bits: accept any column whose bf16 logit equals the row maximum
+    picked = logits16.gather(1, got_tok[:, None])[:, 0]
+    assert (picked >= logits16.max(1).values - 1e-2 * logits16.abs().max()).all()
+    assert (got_tok == want_tok).float().mean().item() >= 0.75
+    eos = int(want_tok[0])
+    assert (fin[:M] == (got_tok == eos).int()).all() and (fin[M:] == 0).all()
+    st = state.tolist()
+    assert st[0] == 3 and st[2] == 1 and st[1] == (2 if bool((got_tok == eos).all()) else -1)
+
+
+@pytest.mark.parametrize("B,H,Sk,split_cache", [(16, 16, 2509, False), (3, 12, 77, False), (16, 16, 37, True), (2, 4, 1, True)])
+def test_decode_attention(cuda_lib, B, H, Sk, split_cache):
+    """One query per (page, head) against strided K | V: cross-attention form (fixed key count, cluster key splits) and
+    self-attention form (key count = device position + 1, pad keys hidden through the generated ids)."""
+    from pixparse_b200 import ops
+    torch.manual_seed(4)
+    D = H * 64
+    t_max = 64 if split_cache else Sk
+    q = torch.randn((B, D), device=DEV).bfloat16()
+    kv = torch.randn((B, t_max, 2 * D), device=DEV).bfloat16()
+    out = torch.zeros((B, D), device=DEV, dtype=torch.bfloat16)
+    qf = q.float().view(B, H, 1, 64)
+    kf = kv[:, :Sk, :D].float().reshape(B, Sk, H, 64).transpose(1, 2)
+    vf = kv[:, :Sk, D:].float().reshape(B, Sk, H, 64).transpose(1, 2)
+    if split_cache:
+        pos = torch.tensor([Sk - 1], device=DEV, dtype=torch.int32)
+        ids = torch.randint(3, 100, (B, t_max + 1), device=DEV)
+        if Sk > 4:
+            ids[:, 2] = 1
+            ids[0, 4] = 1
+        ops.decode_attention(q, kv, kv, out, B=B, H=H, ld_kv=2 * D, kv_bstride=t_max * 2 * D, v_col0=D, pos=pos,
+                             key_ids=ids, pad_id=1)
+        mask = ids[:, :Sk].ne(1)[:, None, None, :]
+    else:
+        ops.decode_attention(q, kv.view(B * t_max, 2 * D), kv.view(B * t_max, 2 * D), out, B=B, H=H, ld_kv=2 * D,
+                             kv_bstride=t_max * 2 * D, v_col0=D, sk=Sk)
+        mask = None
+    ref = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask).reshape(B, D)
+    assert rel_err(out, ref) < 8e-3      # bf16 probabilities and output
+
+
+def test_decode_embed(cuda_lib):
+    from pixparse_b200 import ops
+    torch.manual_seed(6)
+    B, D, V = 5, 256, 300
+    tok, pe = torch.randn((V, D), device=DEV), torch.randn((40, D), device=DEV)
+    ids = torch.randint(0, V, (B, 20), device=DEV)
+    pos = torch.tensor([7], device=DEV, dtype=torch.int32)
+    x = torch.zeros((B, D), device=DEV)
+    ops.decode_embed(ids, pos, tok, pe, x, pos_offset=2, scale=1.5)
+    assert torch.allclose(x, tok[ids[:, 7]] * 1.5 + pe[9], atol=1e-6)
