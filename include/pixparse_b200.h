@@ -290,7 +290,7 @@ int b200_adamw_step(const B200AdamWArgs* args, void* stream);
  * decode_linear: y[M, N] = x[M, K] W[N, K]^T (+ bias) (act = 1: GELU on the bf16-rounded pre-activation) (+ fp32 resid);
  *   outputs bf16 and/or fp32 with row pitch ldo, shifted by (*pos) * out_pos_stride elements when pos != NULL (appending
  *   K | V to a [B, T_max, 2D] cache). With argmax_partial != NULL nothing is stored: the per-CTA (max, argmax) of the
- *   bf16-rounded outputs is written as [b200_decode_linear_ctas(N)][16] packed 64-bit keys (LM head fused with argmax).
+ *   bf16-rounded outputs is written as [16][b200_decode_linear_ctas(N)] packed 64-bit keys (LM head fused with argmax).
  * decode_attention: one query per (page, head): q [B, ldq], K / V rows ld_kv apart, pages kv_bstride apart; the key
  *   count is sk, or (*pos) + 1 when pos != NULL; key j of page b is hidden when key_ids[b * ld_ids + j] == pad_id
  *   (attention_mask = input_ids.ne(pad), models/text_decoder_hf.py:68).

@@ -23,10 +23,8 @@ namespace cg = cooperative_groups;
 
 namespace b200 {
 
-constexpr int DL_WARPS = 8;        // warps per CTA
-constexpr int DL_R = 2;            // weight rows (output columns) per warp
-constexpr int DL_M = 16;           // activation rows per launch
-constexpr int DL_COLS = DL_WARPS * DL_R;
+constexpr int DL_WARPS = 8;        // warps per CTA: they split K in 32-element chunks (chunk c goes to warp c % 8)
+constexpr int DL_M = 16;           // activation rows per launch = the M of one mma.m16n8k16
 
 __device__ __forceinline__ unsigned long long argmax_pack(float v, int n) {
   // monotonic map of the float's bits, then the column index inverted: larger key = larger value, ties -> smaller index
@@ -42,90 +40,117 @@ struct DecodeLinearParams {
   const float* resid; long long ld_resid;
   bf16* out16; float* out32; long long ldo;
   const int* pos; long long out_pos_stride;      // outputs are shifted by *pos * out_pos_stride elements (KV-cache append)
-  unsigned long long* argmax_partial;            // [gridDim.x][DL_M] when mode == argmax
+  unsigned long long* argmax_partial;            // [DL_M][gridDim.x] when mode == argmax
   int M, N, K, act;
 };
 
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// read-once data (weights): non-coherent load without L1 allocation
+__device__ __forceinline__ uint4 ld_nc_na(const uint4* ptr) {
+  uint4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+
+// y[16, N] = x[16, K] W[N, K]^T for the <= 16 pages of a decode step. The work is reading W once, so the kernel is built
+// around bytes in flight, not math: a CTA owns 8 G weight rows, its 8 warps split K, and every lane fetches 16-byte pieces of
+// W with plain coalesced loads (4 lanes = 64 contiguous bytes of one row) that are ALL issued before the first use. The
+// 16 x 8 x 16 warp-level MMA does the arithmetic straight from those registers -- the reduction index of a dot product may be
+// permuted freely, so the lane's 8 consecutive weights ARE two B fragments as loaded (k-steps {.x,.y} and {.z,.w}) provided the
+// activation fragments use the same permutation (two 16-byte loads of rows g and g + 8 at the same k). No shared-memory
+// staging, no conversions, no shuffles in the main loop; partial sums of the 8 warps meet in shared memory.
+// (tcgen05 needs M = 128 and operands staged in shared memory -- for 16 rows bound by HBM it would only add latency.)
+template <int G>
 __global__ void __launch_bounds__(DL_WARPS * 32)
 decode_linear_kernel(const DecodeLinearParams p) {
-  __shared__ unsigned long long s_best[DL_WARPS][DL_M];
+  constexpr int U = G == 4 ? 2 : 4;      // chunks in flight per warp and loop trip
+  constexpr int NC = 8 * G;              // output columns per CTA
+  __shared__ float s_red[DL_WARPS][DL_M][NC + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * DL_WARPS + warp) * DL_R;
-  f32x2 acc[DL_R][DL_M];
+  const int g8 = lane >> 2, j = lane & 3;
+  const int n_base = blockIdx.x * NC;
+  float acc[G][4];
 #pragma unroll
-  for (int r = 0; r < DL_R; ++r)
+  for (int gi = 0; gi < G; ++gi)
 #pragma unroll
-    for (int m = 0; m < DL_M; ++m) acc[r][m] = f2_splat(0.f);
-  if (n0 < p.N) {
-    const bf16* w0 = p.w + (long long)n0 * p.ldw;
-    const bool has1 = n0 + 1 < p.N;
-    const bf16* w1 = has1 ? w0 + p.ldw : w0;
-#pragma unroll 2
-    for (int k0 = lane * 8; k0 < p.K; k0 += 256) {
-      const uint4 wa = __ldg(reinterpret_cast<const uint4*>(w0 + k0));
-      const uint4 wb = __ldg(reinterpret_cast<const uint4*>(w1 + k0));
-      const f32x2 a0 = f2_pack(bf16_lo(wa.x), bf16_hi(wa.x)), a1 = f2_pack(bf16_lo(wa.y), bf16_hi(wa.y));
-      const f32x2 a2 = f2_pack(bf16_lo(wa.z), bf16_hi(wa.z)), a3 = f2_pack(bf16_lo(wa.w), bf16_hi(wa.w));
-      const f32x2 b0 = f2_pack(bf16_lo(wb.x), bf16_hi(wb.x)), b1 = f2_pack(bf16_lo(wb.y), bf16_hi(wb.y));
-      const f32x2 b2 = f2_pack(bf16_lo(wb.z), bf16_hi(wb.z)), b3 = f2_pack(bf16_lo(wb.w), bf16_hi(wb.w));
+    for (int i = 0; i < 4; ++i) acc[gi][i] = 0.f;
+  const int nchunks = (p.K + 31) >> 5;
+  // every load is unconditional (addresses clamped into the operands): rows >= M and columns >= N compute garbage that the
+  // epilogue never stores, chunks past K are cancelled by zeroing the activation fragment. Unpredicated loads are what the
+  // compiler hoists to the top of the trip, so a warp's U * (G + 2) 16-byte loads are in flight together.
+  const bf16* xa_row = p.x + (long long)min(g8, p.M - 1) * p.ldx + j * 8;
+  const bf16* xb_row = p.x + (long long)min(g8 + 8, p.M - 1) * p.ldx + j * 8;
+  const bf16* w_row[G];
 #pragma unroll
-      for (int m = 0; m < DL_M; ++m) {
-        if (m < p.M) {      // (uniform: M is a launch constant)
-          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + (long long)m * p.ldx + k0));
-          const f32x2 x0 = f2_pack(bf16_lo(xv.x), bf16_hi(xv.x)), x1 = f2_pack(bf16_lo(xv.y), bf16_hi(xv.y));
-          const f32x2 x2 = f2_pack(bf16_lo(xv.z), bf16_hi(xv.z)), x3 = f2_pack(bf16_lo(xv.w), bf16_hi(xv.w));
-          acc[0][m] = f2_fma(a0, x0, f2_fma(a1, x1, f2_fma(a2, x2, f2_fma(a3, x3, acc[0][m]))));
-          acc[1][m] = f2_fma(b0, x0, f2_fma(b1, x1, f2_fma(b2, x2, f2_fma(b3, x3, acc[1][m]))));
-        }
+  for (int gi = 0; gi < G; ++gi) w_row[gi] = p.w + (long long)min(n_base + gi * 8 + g8, p.N - 1) * p.ldw + j * 8;
+  const int last_chunk = nchunks - 1;
+  for (int c0 = warp; c0 < nchunks; c0 += DL_WARPS * U) {
+    uint4 xa[U], xb[U], wv[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = min(c0 + DL_WARPS * u, last_chunk) * 32;
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) wv[u][gi] = ld_nc_na(reinterpret_cast<const uint4*>(w_row[gi] + k));
+      xa[u] = __ldg(reinterpret_cast<const uint4*>(xa_row + k));
+      xb[u] = __ldg(reinterpret_cast<const uint4*>(xb_row + k));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + DL_WARPS * u > last_chunk) xa[u] = xb[u] = make_uint4(0u, 0u, 0u, 0u);      // (warp-uniform)
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        mma_bf16_16816(acc[gi], xa[u].x, xb[u].x, xa[u].y, xb[u].y, wv[u][gi].x, wv[u][gi].y);
+        mma_bf16_16816(acc[gi], xa[u].z, xb[u].z, xa[u].w, xb[u].w, wv[u][gi].z, wv[u][gi].w);
       }
     }
   }
-  // warp reduction: afterwards lane m holds row m's two dot products
-  float mine[DL_R] = {0.f, 0.f};
+  // accumulator fragment: c0, c1 = (row g8, cols 2j, 2j + 1), c2, c3 = (row g8 + 8, same cols)
 #pragma unroll
-  for (int r = 0; r < DL_R; ++r)
-#pragma unroll
-    for (int m = 0; m < DL_M; ++m) {
-      float lo, hi;
-      f2_unpack(acc[r][m], lo, hi);
-      const float s = warp_sum(lo + hi);
-      if (lane == m) mine[r] = s;
-    }
-  const int m = lane;
-  const bool row_ok = m < p.M;
-  if (p.argmax_partial != nullptr) {
-    // LM head: logits are what the teacher-forced path would have stored (bf16), compared without leaving the chip
-    unsigned long long best = 0ull;
-    if (row_ok) {
-#pragma unroll
-      for (int r = 0; r < DL_R; ++r)
-        if (n0 + r < p.N) {
-          const unsigned long long c = argmax_pack(round_bf16(mine[r]), n0 + r);
-          best = c > best ? c : best;
-        }
-    }
-    if (lane < DL_M) s_best[warp][lane] = best;
-    __syncthreads();
-    if (threadIdx.x < DL_M) {
-      unsigned long long b = 0ull;
-#pragma unroll
-      for (int w = 0; w < DL_WARPS; ++w) b = s_best[w][threadIdx.x] > b ? s_best[w][threadIdx.x] : b;
-      p.argmax_partial[(long long)blockIdx.x * DL_M + threadIdx.x] = b;
-    }
-    return;
+  for (int gi = 0; gi < G; ++gi) {
+    s_red[warp][g8][gi * 8 + 2 * j] = acc[gi][0];
+    s_red[warp][g8][gi * 8 + 2 * j + 1] = acc[gi][1];
+    s_red[warp][g8 + 8][gi * 8 + 2 * j] = acc[gi][2];
+    s_red[warp][g8 + 8][gi * 8 + 2 * j + 1] = acc[gi][3];
   }
-  if (!row_ok || n0 >= p.N) return;
-  const long long shift = p.pos != nullptr ? (long long)(*p.pos) * p.out_pos_stride : 0;
+  __syncthreads();
+  const long long shift = (p.pos != nullptr && p.argmax_partial == nullptr) ? (long long)(*p.pos) * p.out_pos_stride : 0;
+  for (int o = threadIdx.x; o < DL_M * NC; o += DL_WARPS * 32) {      // (whole warps enter or skip: NC divides 32)
+    const int m = o / NC, nl = o % NC, n = n_base + nl;
+    float v = 0.f;
 #pragma unroll
-  for (int r = 0; r < DL_R; ++r) {
-    const int n = n0 + r;
-    if (n >= p.N) break;
-    float v = mine[r] + (p.bias != nullptr ? __ldg(p.bias + n) : 0.f);
+    for (int w = 0; w < DL_WARPS; ++w) v += s_red[w][m][nl];
+    if (p.argmax_partial != nullptr) {
+      // LM head: the logit the teacher-forced path would have stored (bf16), compared without leaving the chip
+      unsigned long long key = (n < p.N) ? argmax_pack(round_bf16(v), n) : 0ull;
+#pragma unroll
+      for (int off = NC / 2; off > 0; off >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, off);
+        key = other > key ? other : key;
+      }
+      if (nl == 0) p.argmax_partial[(long long)m * gridDim.x + blockIdx.x] = key;
+      continue;
+    }
+    if (m >= p.M || n >= p.N) continue;
+    if (p.bias != nullptr) v += __ldg(p.bias + n);
     if (p.act == 1) v = gelu_erf(round_bf16(v));      // nn.GELU on the bf16 pre-activation, as the GEMM epilogue does
     if (p.resid != nullptr) v += p.resid[(long long)m * p.ld_resid + n];
     if (p.out32 != nullptr) p.out32[shift + (long long)m * p.ldo + n] = v;
     if (p.out16 != nullptr) p.out16[shift + (long long)m * p.ldo + n] = __float2bfloat16_rn(v);
   }
+}
+
+// groups of 8 weight rows per CTA: as many as still leave >= 2 CTAs per SM (small layers run at G = 1: 128 CTAs for N = 1024)
+static int decode_linear_groups(int n) {
+  const int want = 2 * num_sms();
+  if ((n + 31) / 32 >= want) return 4;
+  if ((n + 15) / 16 >= want) return 2;
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -175,13 +200,11 @@ decode_attention_kernel(const DecodeAttnParams p) {
     uint4 kk[8], vv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int key = kb + 4 * i + g;
-      kk[i] = make_uint4(0u, 0u, 0u, 0u);
-      vv[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (key < Sk) {
-        kk[i] = __ldg(reinterpret_cast<const uint4*>(kbase + (long long)key * p.ld_kv));
-        vv[i] = __ldg(reinterpret_cast<const uint4*>(vbase + (long long)key * p.ld_kv));
-      }
+      // unconditional loads (keys past the end re-read the last key: its score is masked below, so its V row, which is
+      // finite, is weighted by 0): unpredicated loads are hoisted together, all 16 of a block are in flight at once
+      const int key = min(kb + 4 * i + g, Sk - 1);
+      kk[i] = ld_nc_na(reinterpret_cast<const uint4*>(kbase + (long long)key * p.ld_kv));
+      vv[i] = ld_nc_na(reinterpret_cast<const uint4*>(vbase + (long long)key * p.ld_kv));
     }
     const int my_key = kb + 4 * c + g;
     bool valid = my_key < Sk;
@@ -201,10 +224,11 @@ decode_attention_kernel(const DecodeAttnParams p) {
       r += __shfl_xor_sync(0xffffffffu, r, 4);
       if (i == c && valid) s = r;
     }
+    // (no early-out for a fully hidden block: a branch here makes the V loads conditional and the compiler sinks them below
+    // the softmax, one more serialised DRAM round trip per block)
     const float m_new = fmaxf(m_run, warp_max(s));
-    if (m_new == -INFINITY) continue;      // (warp-uniform) nothing visible yet
     const float pr = valid ? ex2_approx(s - m_new) : 0.f;
-    const float alpha = ex2_approx(m_run - m_new);      // 0 on the first visible block (m_run = -inf)
+    const float alpha = m_new == -INFINITY ? 1.f : ex2_approx(m_run - m_new);      // 0 on the first visible block (m_run = -inf)
     l_run = l_run * alpha + warp_sum(pr);
     const f32x2 al = f2_splat(alpha);
     a0 = f2_mul(a0, al); a1 = f2_mul(a1, al); a2 = f2_mul(a2, al); a3 = f2_mul(a3, al);
@@ -299,7 +323,7 @@ decode_finalize_kernel(const unsigned long long* __restrict__ partial, int n_cta
   if (warp < B) {
     unsigned long long best = 0ull;
     for (int c = lane; c < n_cta; c += 32) {
-      const unsigned long long v = partial[(long long)c * DL_M + warp];
+      const unsigned long long v = partial[(long long)warp * n_cta + c];
       best = v > best ? v : best;
     }
 #pragma unroll
@@ -334,7 +358,8 @@ extern "C" int b200_decode_linear(const B200DecodeLinearArgs* a, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(a->x && a->w && a->m > 0 && a->n > 0 && a->k > 0, "b200_decode_linear: bad arguments");
   B200_CHECK_ARG(a->m <= DL_M, "b200_decode_linear: at most %d activation rows per call (got %d)", DL_M, a->m);
-  B200_CHECK_ARG(a->k % 8 == 0 && a->ldx % 8 == 0 && a->ldw % 8 == 0, "b200_decode_linear: K, ldx, ldw must be multiples of 8");
+  B200_CHECK_ARG(a->k % 32 == 0 && a->ldx % 8 == 0 && a->ldw % 8 == 0,
+                 "b200_decode_linear: K must be a multiple of 32, ldx and ldw multiples of 8");
   B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w)) & 15) == 0,
                  "b200_decode_linear: x and w must be 16-byte aligned");
   B200_CHECK_ARG(a->argmax_partial != nullptr || a->out_bf16 != nullptr || a->out_f32 != nullptr,
@@ -348,13 +373,19 @@ extern "C" int b200_decode_linear(const B200DecodeLinearArgs* a, void* stream) {
   p.pos = a->pos; p.out_pos_stride = a->out_pos_stride;
   p.argmax_partial = reinterpret_cast<unsigned long long*>(a->argmax_partial);
   p.M = a->m; p.N = a->n; p.K = a->k; p.act = a->act;
-  const int grid = (a->n + DL_COLS - 1) / DL_COLS;
-  decode_linear_kernel<<<grid, DL_WARPS * 32, 0, s>>>(p);
+  const int G = decode_linear_groups(a->n);
+  const int grid = (a->n + 8 * G - 1) / (8 * G);
+  if (G == 4) decode_linear_kernel<4><<<grid, DL_WARPS * 32, 0, s>>>(p);
+  else if (G == 2) decode_linear_kernel<2><<<grid, DL_WARPS * 32, 0, s>>>(p);
+  else decode_linear_kernel<1><<<grid, DL_WARPS * 32, 0, s>>>(p);
   B200_CHECK_LAUNCH("decode_linear");
   return 0;
 }
 
-extern "C" int b200_decode_linear_ctas(int n) { return (n + DL_COLS - 1) / DL_COLS; }
+extern "C" int b200_decode_linear_ctas(int n) {
+  const int G = decode_linear_groups(n);
+  return (n + 8 * G - 1) / (8 * G);
+}
 
 extern "C" int b200_decode_attention(const B200DecodeAttentionArgs* a, void* stream) {
   B200_CHECK_STRUCT(a, B200DecodeAttentionArgs, "b200_decode_attention");

@@ -50,7 +50,7 @@ class GreedyDecodeSession:
         self.u32 = z(B, D, dt=f32)
         self.mean, self.rstd = z(B, dt=f32), z(B, dt=f32)
         self.n_cta = ops.decode_linear_ctas(self.V)
-        self.partial = torch.zeros((self.n_cta, MAX_PAGES), device=dev, dtype=torch.int64)
+        self.partial = torch.zeros((MAX_PAGES, self.n_cta), device=dev, dtype=torch.int64)
         self.graph = None
         self.kernels_per_step = 0
         self.eos_id = None

@@ -1,6 +1,8 @@
 """cruller_large_6layers graph decode of N tokens for 16 pages (for `ncu -k regex:decode_` launch lists / full captures).
 Prints the event-timed ms per token step as well."""
+import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pixparse_b200 import synthetic
 from pixparse_b200.framework import DeviceEnv

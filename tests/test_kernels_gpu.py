@@ -482,7 +482,7 @@ def test_decode_linear(cuda_lib, M, N, K):
     assert rel_err(out16[:M], want) < 4e-3
     # fused argmax (LM head): partial keys -> finalize appends the token at ids[:, pos + 1]
     n_cta = ops.decode_linear_ctas(N)
-    partial = torch.zeros((n_cta, 16), device=DEV, dtype=torch.int64)
+    partial = torch.zeros((16, n_cta), device=DEV, dtype=torch.int64)
     ops.decode_linear(x, w, M=M, argmax_partial=partial)
     ids = torch.zeros((M, 8), device=DEV, dtype=torch.int64)
     state = torch.tensor([2, -1, 0, 0], device=DEV, dtype=torch.int32)
