@@ -357,7 +357,14 @@ def time_train_config(cfgname, env, steps, warmup, batch=None, dropout_off=False
     e1.record()
     barrier()
     launches = _lib.launch_count()
+    own_ms = e0.elapsed_time(e1) / steps
     ms_step = max_over_ranks(e0.elapsed_time(e1)) / steps
+    per_rank = [own_ms]
+    if world > 1:      # every rank's own device time (diagnostic: box-internal GPU-to-GPU spread vs exchange cost)
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[env.global_rank] = own_ms
+        dist.all_reduce(t)
+        per_rank = [round(float(x), 3) for x in t.tolist()]
     loss_val = float(last[1].item())
 
     # ---- end to end through the Task API: pinned host batch -> train_step -> loss read back
@@ -373,7 +380,7 @@ def time_train_config(cfgname, env, steps, warmup, batch=None, dropout_off=False
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / steps
     sampler.stop()
     res = {"task": task, "device_step": device_step, "barrier": barrier, "B": B, "ms_step": ms_step, "ms_e2e": ms_e2e,
-           "loss": loss_val, "launches": launches, "h2d_bytes": h2d_bytes, "clocks": sampler.summary(),
+           "loss": loss_val, "launches": launches, "per_rank_ms": per_rank, "h2d_bytes": h2d_bytes, "clocks": sampler.summary(),
            "pages_per_s": world * B / (ms_step * 1e-3), "e2e_pages_per_s": world * B / (ms_e2e * 1e-3)}
     return res
 
@@ -589,6 +596,10 @@ def run_b200_arm(args):
             for ms, n, calls in rows:
                 fh.write(f"{ms:9.3f} ms  {100 * ms / ms_step:5.1f}%  calls={calls:4d}  avg={1e3 * ms / calls:8.1f} us  {n}\n")
             fh.write(f"{sum(r[0] for r in rows):9.3f} ms  total of the above\n")
+            for n in ("b200_gemm_bf16", "b200_attention_fwd", "b200_attention_bwd"):
+                fh.write(f"\n{n} by variant (ms per step, TFLOP/s, calls):\n")
+                for tag, v in sorted(allp[n]["detail"].items(), key=lambda kv: -kv[1]["ms"]):
+                    fh.write(f"{v['ms']:9.3f} ms  {str(v['tflops']):>7} TF/s  calls={v['calls']:3d}  {tag}\n")
     gemm_ms, gemm_flops, gemm_n = prof["b200_gemm_bf16"]["ms"], prof["b200_gemm_bf16"]["flops"], prof["b200_gemm_bf16"]["calls"]
     att_ms = prof["b200_attention_fwd"]["ms"] + prof["b200_attention_bwd"]["ms"]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
@@ -643,6 +654,7 @@ def run_b200_arm(args):
                 "vs_nominal_2250": pages_per_s * gflop / 1e3 / (world * 2250.0)},
         "loss": res["loss"],
         "clocks": res["clocks"],
+        "per_rank_ms": res["per_rank_ms"],
         "e2e": {"value": res["e2e_pages_per_s"], "unit": "pages/s", "ms_per_step": res["ms_e2e"],
                 "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": 4},
         "gpu_launches": res["launches"],

@@ -235,6 +235,11 @@ int b200_embed_fwd(const long long* ids, const float* tok_emb, const float* pos_
 int b200_embed_bwd(const long long* ids, const float* dx, float* d_tok_emb, float* d_pos_emb, int B, int T, int D,
                    int pos_offset, float scale, long long padding_idx, void* stream);
 int b200_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* dst[i] = (dst[i] + sum_{s != skip} stage[s * stride + i]) * scale for i < n: the local reduction of the copy-engine
+ * gradient exchange that stands in for DistributedDataParallel's all-reduce (task/task_cruller_pretrain.py:181-189):
+ * dst = this rank's share of a gradient bucket, stage = the copies of that share its peers pushed over NVLink */
+int b200_reduce_shards(float* dst, const float* stage, long long stride, int nsrc, int skip, float scale, long long n,
+                       void* stream);
 
 /* ---- loss + optimizer ------------------------------------------------------------------------------
  * nn.CrossEntropyLoss(ignore_index) fwd+bwd in one pass (task_cruller_pretrain.py:118,251-254):

@@ -145,6 +145,7 @@ SIGNATURES = {
     "b200_embed_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "b200_embed_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _L, _P],
     "b200_cast_f32_bf16": [_P, _P, _L, _P],
+    "b200_reduce_shards": [_P, _P, _L, _I, _I, _F, _L, _P],
     "b200_ce_prepare": [_P, _I, _L, _P, _P],
     "b200_ce_fwd_bwd": [_P, _L, _P, _P, _L, _P, _P, _I, _I, _L, _F, _P],
     "b200_grad_norm": [_P, _L, _P, _P, _F, _F, _P],
@@ -198,6 +199,7 @@ def stream():
 # kernels launched per C-ABI call (grad_norm: partial + final; attention_bwd: prep + main + dq convert)
 _KERNELS_PER_CALL = {"b200_grad_norm": 2, "b200_attention_bwd": 3}
 _launches = 0
+_profile_shapes = bool(int(os.environ.get("PIXPARSE_B200_PROFILE_SHAPES", "0")))      # per-(M, N, K) GEMM rows in profiles
 _profile = None     # {name: [(start_event, end_event, flops), ...]} while profile_ops() is active
 
 
@@ -232,6 +234,8 @@ def call(name, *args):
         if isinstance(a0, GemmArgs):
             flops = 2.0 * a0.m * a0.n * a0.k
             tag = f"gemm a_mn={a0.a_mn_major} b_mn={a0.b_mn_major} epi={a0.epilogue}"
+            if _profile_shapes:
+                tag += f" M={a0.m} N={a0.n} K={a0.k}"
         elif isinstance(a0, AttentionFwdArgs):      # full Sq x Sk (bench.py / BASELINE.md convention), head_dim 64
             flops = 4.0 * a0.batch * a0.heads * a0.sq * a0.sk * 64
             tag = f"attention_fwd Sq={a0.sq} Sk={a0.sk} causal={a0.causal} drop={int(a0.drop_p > 0)}"

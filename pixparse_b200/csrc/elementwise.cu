@@ -258,6 +258,47 @@ extern "C" int b200_embed_bwd(const long long* ids, const float* dx, float* d_to
   return 0;
 }
 
+// dst[i] = (dst[i] + sum_{s != skip} stage[s * stride + i]) * scale: the reduction step of the copy-engine gradient exchange
+// (pixparse_b200/reducer.py): this rank's share of a gradient bucket plus the copies its peers pushed into the staging area
+namespace b200 {
+__global__ void __launch_bounds__(256)
+reduce_shards_kernel(float* __restrict__ dst, const float* __restrict__ stage, long long stride, int nsrc, int skip,
+                     float scale, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(dst)[i];
+    for (int s = 0; s < nsrc; ++s) {
+      if (s == skip) continue;
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(stage + s * stride) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    float a = dst[i];
+    for (int s = 0; s < nsrc; ++s)
+      if (s != skip) a += stage[s * stride + i];
+    dst[i] = a * scale;
+  }
+}
+}  // namespace b200
+
+extern "C" int b200_reduce_shards(float* dst, const float* stage, long long stride, int nsrc, int skip, float scale,
+                                  long long n, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  B200_CHECK_ARG(n >= 0 && nsrc >= 1 && stride >= 0, "b200_reduce_shards: bad arguments");
+  if (n == 0) return 0;
+  B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(stage)) & 15) == 0 && stride % 4 == 0,
+                 "b200_reduce_shards: pointers must be 16-byte aligned and the stride a multiple of 4 elements");
+  // a small grid: the kernel runs between persistent GEMM / attention kernels that own every SM
+  const long long want = (n / 4 + 255) / 256;
+  const int grid = (int)(want < 1 ? 1 : (want > 2LL * b200::num_sms() ? 2LL * b200::num_sms() : want));
+  b200::reduce_shards_kernel<<<grid, 256, 0, s>>>(dst, stage, stride, nsrc, skip, scale, n);
+  B200_CHECK_LAUNCH("reduce_shards");
+  return 0;
+}
+
 extern "C" int b200_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(n >= 0, "b200_cast_f32_bf16: negative size");

@@ -86,6 +86,16 @@ class ParamArena:
     def sync_shadow(self):
         ops.cast_bf16(self.p32, self.p16)
 
+    def replace_grad_buffer(self, new):
+        """Move the gradient arena into `new` (same size; e.g. a peer-addressable symmetric-memory allocation)."""
+        assert new.numel() == self.total and new.dtype == torch.float32 and new.device == self.g32.device
+        new.copy_(self.g32)
+        self.g32 = new
+        with torch.no_grad():
+            for key, p in zip(self.keys, self.params):
+                o, n, shape = self.index[key]
+                p.grad = self.g32[o:o + n].view(shape)
+
 
 def engine_for(module):
     """Engine of the Cruller that owns `module` (created lazily; sub-modules share their parent's engine)."""

@@ -199,6 +199,13 @@ def cast_bf16(src, dst=None):
     return dst
 
 
+def reduce_shards(dst, stage, stride, nsrc, skip, scale):
+    """dst (fp32, flat) = (dst + sum over the nsrc slots of `stage` except `skip`, `stride` elements apart) * scale."""
+    assert dst.dtype == F32 and stage.dtype == F32 and dst.is_contiguous()
+    call("b200_reduce_shards", ptr(dst), ptr(stage), int(stride), int(nsrc), int(skip), float(scale), dst.numel(), stream())
+    return dst
+
+
 def cross_entropy(logits, targets, vocab, *, dlogits=None, grad_scale=1.0, ignore_index=-100, row_loss=None,
                   stats=None):
     """logits: [rows, ld] bf16 (ld >= vocab rounded up to 8). Returns stats tensor: [n_valid, mean_loss].

@@ -83,7 +83,10 @@ class GradReducer:
         else:
             self._issue(*self._pending)
             self._pending = [lo, hi]
-        if self._pending[1] - self._pending[0] >= self.bucket_elems:
+        # a full bucket goes out; so does anything that reaches into the first bucket's worth of the arena -- backward ends
+        # there (ranges arrive in descending address order), and whatever is still pending at that point is exchanged
+        # with nothing left to hide it
+        if self._pending[1] - self._pending[0] >= self.bucket_elems or self._pending[0] < self.bucket_elems:
             self._issue(*self._pending)
             self._pending = None
 
@@ -107,3 +110,155 @@ class GradReducer:
             self._issue(lo, hi)
         if self.cuda and self.world_size > 1:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Copy-engine gradient exchange over NVLink / NVSwitch
+# ----------------------------------------------------------------------------------------------------------------------
+class _SymmetricTransport:
+    """Peer-addressable buffers through torch symmetric memory (CUDA VMM handles exchanged at rendezvous): a ``copy_``
+    into a peer's buffer is a device-to-device memcpy that the COPY ENGINES carry over NVLink -- no SM is involved."""
+
+    def __init__(self, numel_by_name, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.group = group if group is not None else dist.group.WORLD
+        self.local, self.peer = {}, {}
+        for name, numel in numel_by_name.items():
+            t = symm.empty(numel, dtype=torch.float32, device=device)
+            t.zero_()
+            hdl = symm.rendezvous(t, self.group)
+            self.local[name] = t
+            self.peer[name] = [t if r == self.rank else hdl.get_buffer(r, (numel,), torch.float32) for r in range(self.world)]
+        self._flag = torch.zeros(1, device=device)
+
+    def push(self, peer, name, offset, src):
+        self.peer[name][peer][offset:offset + src.numel()].copy_(src, non_blocking=True)
+
+    def barrier(self):
+        # every rank's earlier pushes (same stream, in order) have landed once this tiny all-reduce completes anywhere
+        dist.all_reduce(self._flag, group=self.group)
+
+
+class _ExchangeTransport:
+    """Test double for world_size > 1 WITHOUT peer memory (gloo on CPU): pushes are queued and delivered at the next
+    barrier through an object all-gather. Exercises the bucket / share arithmetic and the ordering of the protocol."""
+
+    def __init__(self, numel_by_name, device, group):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.group = group
+        self.local = {name: torch.zeros(numel, device=device) for name, numel in numel_by_name.items()}
+        self._queue = []
+
+    def push(self, peer, name, offset, src):
+        self._queue.append((peer, name, offset, src.detach().cpu().clone()))
+
+    def barrier(self):
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, self._queue, group=self.group)
+        self._queue = []
+        for q in everyone:
+            for peer, name, offset, data in q:
+                if peer == self.rank:
+                    self.local[name][offset:offset + data.numel()].copy_(data)
+
+
+class P2PGradReducer(GradReducer):
+    """Gradient mean over ranks WITHOUT collective kernels: what DistributedDataParallel's bucketed all-reduce
+    (/root/reference/src/pixparse/task/task_cruller_pretrain.py:181-189) computes, moved onto the copy engines.
+
+    Why: every GEMM / attention kernel of the step is persistent and owns all 148 SMs. An NCCL all-reduce needs SMs of its
+    own, so it either waits for kernel boundaries or takes SMs away from kernels whose tiles were dealt out for 148 of them
+    (measured on 2 B200s: 640 MB of all-reduces under a stream of GEMMs cost the GEMMs +16 %; the same bytes pushed by the
+    copy engines +1.5 % -- profiles/r02_p2p_probe.txt). The exchange therefore uses the one resource backward leaves idle:
+      1. each bucket [lo, hi) of the flat gradient arena is cut into `world` shares; rank r owns share r,
+      2. every rank PUSHES share p of its gradients into a staging slot on peer p (copy engine, NVLink),
+      3. after a barrier the owner sums its share with the `world - 1` staged copies and scales by 1 / world
+         (b200_reduce_shards: one small memory-bound kernel),
+      4. the owner pushes the finished share into every peer's gradient arena (copy engine again),
+    i.e. reduce-scatter + all-gather, per bucket, in the order backward finishes the buckets, on a side stream. Only the
+    barriers (1-element NCCL all-reduces) and the local sum touch an SM. Every rank ends with bit-identical averaged
+    gradients (each share is summed on exactly one rank), so clipping and AdamW stay replicated and unchanged."""
+
+    def __init__(self, arena, process_group=None, bucket_bytes=64 << 20, transport=None):
+        super().__init__(arena.g32, process_group, bucket_bytes)
+        assert self.world_size > 1
+        self.rank = dist.get_rank(process_group)
+        total = arena.g32.numel()
+        # staging area: per bucket `world` slots of one share each (shares are rounded up to 64 elements)
+        self.stage_numel = total + self.world_size * 64 * 512
+        sizes = {"grad": total, "stage": self.stage_numel}
+        if transport is None:
+            transport = _SymmetricTransport if self.cuda else _ExchangeTransport
+        self.tr = transport(sizes, arena.g32.device, process_group)
+        # the gradient arena itself must be peer-addressable (step 4 writes into it): move it into the symmetric buffer
+        arena.replace_grad_buffer(self.tr.local["grad"])
+        self.flat = arena.g32
+        self.stage = self.tr.local["stage"]
+        self._cursor = 0
+
+    def begin(self):
+        super().begin()
+        self._cursor = 0
+
+    def shares(self, lo, hi):
+        """[(start, stop)] * world: the share of bucket [lo, hi) each rank owns (64-element granularity, may be empty)."""
+        w = self.world_size
+        c = ((hi - lo + w - 1) // w + 63) // 64 * 64
+        return c, [(min(lo + r * c, hi), min(lo + (r + 1) * c, hi)) for r in range(w)]
+
+    def _exchange(self, lo, hi):
+        from . import ops
+        w, me = self.world_size, self.rank
+        c, shares = self.shares(lo, hi)
+        base = self._cursor
+        self._cursor += w * c
+        if self._cursor > self.stage_numel:
+            raise RuntimeError("gradient staging area exhausted (more than 512 buckets in one step?)")
+        for d in range(1, w):                      # staggered, so that at any moment every peer is some rank's target
+            p = (me + d) % w
+            a, b = shares[p]
+            if b > a:
+                self.tr.push(p, "stage", base + me * c, self.flat[a:b])
+        self.tr.barrier()
+        a, b = shares[me]
+        if b > a:
+            if self.cuda:
+                ops.reduce_shards(self.flat[a:b], self.stage[base:base + w * c], c, w, me, 1.0 / w)
+            else:
+                acc = self.flat[a:b].clone()
+                for s in range(w):
+                    if s != me:
+                        acc += self.stage[base + s * c: base + s * c + (b - a)]
+                self.flat[a:b].copy_(acc / w)
+            for d in range(1, w):
+                self.tr.push((me + d) % w, "grad", a, self.flat[a:b])
+
+    def _all_reduce_mean(self, view):
+        lo = view.storage_offset() - self.flat.storage_offset()
+        self._exchange(lo, lo + view.numel())
+
+    def finish(self):
+        if not self.enabled:
+            return
+        super().finish()
+        if self.world_size > 1:
+            # all step-4 pushes into this rank's arena have landed before the optimizer reads it
+            if self.cuda:
+                with torch.cuda.stream(self.comm_stream):
+                    self.tr.barrier()
+                torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)
+            else:
+                self.tr.barrier()
+
+
+def make_grad_reducer(arena, process_group=None):
+    """The gradient exchange of a data-parallel run: copy-engine pushes over NVLink on B200s (PIXPARSE_B200_REDUCER=p2p,
+    the default with NCCL on CUDA), NCCL all-reduce of arena ranges otherwise (PIXPARSE_B200_REDUCER=nccl, gloo, CPU)."""
+    import os
+    mode = os.environ.get("PIXPARSE_B200_REDUCER", "p2p")
+    if mode == "none":      # diagnostics only: independent replicas, no exchange (the floor of the N-GPU step time)
+        return None
+    if mode == "p2p" and arena.g32.is_cuda and dist.get_backend(process_group) == "nccl":
+        return P2PGradReducer(arena, process_group)
+    return GradReducer(arena.g32, process_group)

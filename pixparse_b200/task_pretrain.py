@@ -10,7 +10,7 @@ runs underneath ``train_step``:
     autocast + Cruller.forward (timm / transformers)     engine.forward_backward: tcgen05 GEMM / attention kernels
     nn.CrossEntropyLoss on materialised fp32 logits      one-pass CE kernel writing dlogits in place (bf16)
     scaler.scale(loss).backward() (autograd)             hand-sequenced backward kernels, fp32 grads in a flat arena
-    DDP reducer (25 MiB buckets)                         GradReducer: NCCL all-reduce of arena ranges under backward
+    DDP reducer (25 MiB buckets)                         reducer.py: copy-engine reduce-scatter / all-gather of arena ranges under backward
     GradScaler.unscale_ + clip_grad_norm_ + AdamW        grad_norm + fused clip/AdamW/bf16-refresh/zero-grad kernels
 
 Numerics are bf16 operands with fp32 accumulation and fp32 master weights, i.e. what the reference gets from
@@ -28,7 +28,7 @@ from .engine import engine_for
 from .framework import DeviceEnv, OptimizationCfg, TaskTrain, TaskTrainCfg
 from .models import Cruller, ModelCfg, get_model_config
 from .optim import FusedAdamW
-from .reducer import GradReducer
+from .reducer import make_grad_reducer
 from .schedule import create_scheduler
 from . import synthetic
 
@@ -134,14 +134,15 @@ class TaskCrullerPretrain(TaskTrain):
         if self.device_env.world_size > 1:
             # all ranks start from rank 0's weights (DDP broadcasts parameters at construction)
             torch.distributed.broadcast(arena.p32, src=0)
-            self.reducer = GradReducer(arena.g32)
+            self.reducer = make_grad_reducer(arena)
             self.has_no_sync = True
 
             def _ready(first_key, last_key, _ar=arena, _r=self.reducer):
                 lo = _ar.index[first_key][0]
                 o, n, _ = _ar.index[last_key]
                 _r.range_ready(lo, o + (n + 63) // 64 * 64)
-            self.engine._grad_ready_hook = _ready
+            if self.reducer is not None:
+                self.engine._grad_ready_hook = _ready
 
         opt = self.cfg.opt
         if opt.optimizer != 'adamw':

@@ -8,7 +8,7 @@ import torch.distributed as dist
 from pixparse_b200 import models, synthetic
 from pixparse_b200.engine import engine_for
 from pixparse_b200.framework import DeviceEnv
-from pixparse_b200.reducer import GradReducer
+from pixparse_b200.reducer import GradReducer, P2PGradReducer
 
 env = DeviceEnv()
 rank, world, dev = env.global_rank, env.world_size, env.device
@@ -40,7 +40,8 @@ sl = slice(rank * B, (rank + 1) * B)
 eng = engine_for(m)
 arena = eng.ensure_bound()
 dist.broadcast(arena.p32, src=0)
-red = GradReducer(arena.g32, bucket_bytes=1 << 20)
+mode = os.environ.get("PIXPARSE_B200_REDUCER", "p2p")
+red = P2PGradReducer(arena, bucket_bytes=1 << 20) if mode == "p2p" else GradReducer(arena.g32, bucket_bytes=1 << 20)
 def ready(first, last, _ar=arena):
     lo = _ar.index[first][0]; o, n, _ = _ar.index[last]
     red.range_ready(lo, o + (n + 63) // 64 * 64)
@@ -66,13 +67,14 @@ if rank == 0:
     rel = ((g_ddp - g1).norm() / g1.norm()).item()
     dl = abs(loss_mean - s1[1].item()) / s1[1].item()
     ok = rel < 2e-3 and dl < 1e-5
-    print(f"ddp_check world={world} model={name}: loss {loss_mean:.6f} vs single {s1[1].item():.6f} (rel {dl:.2e}); "
+    print(f"ddp_check world={world} model={name} reducer={type(red).__name__}: loss {loss_mean:.6f} vs single {s1[1].item():.6f} (rel {dl:.2e}); "
           f"grad rel-L2 diff {rel:.3e}; reducer issued {len(red._done)} ranges -> {'PASS' if ok else 'FAIL'}", flush=True)
 # every rank must hold identical averaged gradients
-chk = g_ddp.double().sum()
+chk = torch.stack([g_ddp.double().sum(), g_ddp.double().abs().sum(), (g_ddp.double() * torch.arange(g_ddp.numel(), device=dev) % 7).sum()])
 lst = [torch.zeros_like(chk) for _ in range(world)]
 dist.all_gather(lst, chk)
-same = all(abs((x - lst[0]).item()) < 1e-9 * max(1.0, abs(lst[0].item())) for x in lst)
+same = all(torch.equal(x, lst[0]) for x in lst) if mode == "p2p" else \
+    all(((x - lst[0]).abs() <= 1e-9 * lst[0].abs().clamp(min=1.0)).all().item() for x in lst)
 if rank == 0:
     print("identical gradients on all ranks:", same, flush=True)
 dist.barrier()

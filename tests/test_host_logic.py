@@ -73,6 +73,39 @@ def _reducer_worker(rank, world, port, tmp):
     ok = ok and torch.allclose(flat2, torch.full((n,), (1 + world) / 2.0))
     obj = env.broadcast_object({"x": 42} if rank == 0 else None)
     ok = ok and obj == {"x": 42}
+    # the copy-engine exchange (reduce-scatter + all-gather by pushes into peer buffers) over the exchange test double:
+    # ragged buckets (shares of 64-element granularity, the last ones short or empty), an unannounced stem, no_sync
+    from pixparse_b200.reducer import P2PGradReducer, _ExchangeTransport
+
+    class _Arena:
+        def __init__(self, g):
+            self.g32 = g
+
+        def replace_grad_buffer(self, new):
+            new.copy_(self.g32)
+            self.g32 = new
+    n3 = 64 * 37 + 5
+    g = torch.Generator().manual_seed(11)
+    base = torch.randn(n3, generator=g)
+    arena = _Arena(base * (rank + 1) + rank)
+    red3 = P2PGradReducer(arena, bucket_bytes=4 * 700, transport=_ExchangeTransport)
+    ok = ok and arena.g32 is red3.flat
+    c, shares = red3.shares(64, 64 + 100)
+    ok = ok and c == 64 and shares == [(64, 128), (128, 164)][:world] + [(164, 164)] * (world - 2)
+    red3.begin()
+    red3.range_ready(64 * 30, n3)
+    red3.range_ready(64 * 9, 64 * 30)
+    red3.range_ready(64 * 8, 64 * 9)
+    red3.range_ready(64, 64 * 8)
+    red3.finish()
+    expect3 = base * (sum(range(1, world + 1)) / world) + sum(range(world)) / world
+    ok = ok and torch.allclose(arena.g32, expect3, atol=1e-6)
+    before = arena.g32.clone()
+    with red3.no_sync():
+        red3.begin()
+        red3.range_ready(0, n3)
+        red3.finish()
+    ok = ok and torch.equal(arena.g32, before)
     with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
         f.write("1" if ok else "0")
     dist.barrier()
