@@ -260,5 +260,10 @@ def make_grad_reducer(arena, process_group=None):
     if mode == "none":      # diagnostics only: independent replicas, no exchange (the floor of the N-GPU step time)
         return None
     if mode == "p2p" and arena.g32.is_cuda and dist.get_backend(process_group) == "nccl":
-        return P2PGradReducer(arena, process_group)
+        try:
+            return P2PGradReducer(arena, process_group)
+        except (RuntimeError, ImportError, AttributeError) as e:      # no peer-addressable memory on this system
+            import warnings
+            warnings.warn(f"pixparse_b200: symmetric memory unavailable ({e!r:.200}); gradient exchange falls back to "
+                          "NCCL all-reduce")
     return GradReducer(arena.g32, process_group)
