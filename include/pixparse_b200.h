@@ -30,6 +30,9 @@ const char* b200_last_error(void);
 int b200_abi_version(void);
 /* 0 when the current device is sm_100 (B200); replaces framework/device.py:112 `assert torch.cuda.device_count()` */
 int b200_device_check(void);
+/* Programmatic dependent launch for the kernels that support it: 1 = on, 0 = off, -1 = follow the environment
+ * (PIXPARSE_B200_PDL, default off). Returns the previous mode. Process-wide; the decode session brackets its step with it. */
+int b200_set_pdl(int mode);
 
 /* ---- GEMM (tcgen05 / TMEM / TMA) ---------------------------------------------------------------
  * D[M,N] = sum_k A(m,k) * B(n,k), bf16 operands, fp32 accumulation in tensor memory.

@@ -144,6 +144,7 @@ SIGNATURES = {
     "b200_tokens_assemble_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "b200_embed_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "b200_embed_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _L, _P],
+    "b200_set_pdl": [_I],
     "b200_cast_f32_bf16": [_P, _P, _L, _P],
     "b200_reduce_shards": [_P, _P, _L, _I, _I, _F, _L, _P],
     "b200_ce_prepare": [_P, _I, _L, _P, _P],

@@ -90,13 +90,26 @@ decode_linear_kernel(const DecodeLinearParams p) {
 #pragma unroll
   for (int gi = 0; gi < G; ++gi) w_row[gi] = p.w + (long long)min(n_base + gi * 8 + g8, p.N - 1) * p.ldw + j * 8;
   const int last_chunk = nchunks - 1;
+  // Programmatic dependent launch: this grid may be resident while its predecessor is still running. The weights do not
+  // depend on it, so the first trip's weight loads go out BEFORE the grid-dependency wait; the activations come after.
+  pdl_launch_dependents();
+  uint4 wv[U][G];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int k = min(warp + DL_WARPS * u, last_chunk) * 32;
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) wv[u][gi] = ld_nc_na(reinterpret_cast<const uint4*>(w_row[gi] + k));
+  }
+  pdl_wait();
   for (int c0 = warp; c0 < nchunks; c0 += DL_WARPS * U) {
-    uint4 xa[U], xb[U], wv[U][G];
+    uint4 xa[U], xb[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int k = min(c0 + DL_WARPS * u, last_chunk) * 32;
+      if (c0 != warp) {      // (warp-uniform) later trips fetch their weights here
 #pragma unroll
-      for (int gi = 0; gi < G; ++gi) wv[u][gi] = ld_nc_na(reinterpret_cast<const uint4*>(w_row[gi] + k));
+        for (int gi = 0; gi < G; ++gi) wv[u][gi] = ld_nc_na(reinterpret_cast<const uint4*>(w_row[gi] + k));
+      }
       xa[u] = __ldg(reinterpret_cast<const uint4*>(xa_row + k));
       xb[u] = __ldg(reinterpret_cast<const uint4*>(xb_row + k));
     }
@@ -180,6 +193,8 @@ decode_attention_kernel(const DecodeAttnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, c = lane & 7;
   const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z, nsplit = gridDim.z;
+  pdl_launch_dependents();      // the next linear may start pulling its weights
+  pdl_wait();                   // q (and the position) come from the predecessors
   const int Sk = p.pos != nullptr ? *p.pos + 1 : p.sk;
   const int nblk = (Sk + 31) >> 5, per = (nblk + nsplit - 1) / nsplit;
   const int blk0 = split * per, blk1 = min(nblk, blk0 + per);
@@ -302,6 +317,8 @@ decode_attention_kernel(const DecodeAttnParams p) {
 __global__ void decode_embed_kernel(const long long* __restrict__ ids, long long ld_ids, const int* __restrict__ pos,
                                     const float* __restrict__ tok_emb, const float* __restrict__ pos_emb,
                                     float* __restrict__ x, int B, int D, int pos_offset, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = *pos;
   const int d4 = D / 4;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * d4; idx += gridDim.x * blockDim.x) {
@@ -319,6 +336,8 @@ decode_finalize_kernel(const unsigned long long* __restrict__ partial, int n_cta
                        long long ld_ids, int* __restrict__ state, int* __restrict__ finished, int B, long long eos_id) {
   __shared__ int s_fin[DL_M];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = state[0];
   if (warp < B) {
     unsigned long long best = 0ull;
@@ -375,9 +394,11 @@ extern "C" int b200_decode_linear(const B200DecodeLinearArgs* a, void* stream) {
   p.M = a->m; p.N = a->n; p.K = a->k; p.act = a->act;
   const int G = decode_linear_groups(a->n);
   const int grid = (a->n + 8 * G - 1) / (8 * G);
-  if (G == 4) decode_linear_kernel<4><<<grid, DL_WARPS * 32, 0, s>>>(p);
-  else if (G == 2) decode_linear_kernel<2><<<grid, DL_WARPS * 32, 0, s>>>(p);
-  else decode_linear_kernel<1><<<grid, DL_WARPS * 32, 0, s>>>(p);
+  cudaError_t err;
+  if (G == 4) err = launch_kernel(decode_linear_kernel<4>, dim3(grid), dim3(DL_WARPS * 32), 0, s, 1, p);
+  else if (G == 2) err = launch_kernel(decode_linear_kernel<2>, dim3(grid), dim3(DL_WARPS * 32), 0, s, 1, p);
+  else err = launch_kernel(decode_linear_kernel<1>, dim3(grid), dim3(DL_WARPS * 32), 0, s, 1, p);
+  B200_CHECK_ARG(err == cudaSuccess, "b200_decode_linear: launch failed: %s", cudaGetErrorString(err));
   B200_CHECK_LAUNCH("decode_linear");
   return 0;
 }
@@ -417,13 +438,18 @@ extern "C" int b200_decode_attention(const B200DecodeAttentionArgs* a, void* str
   cfg.blockDim = dim3(DA_WARPS * 32);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = nsplit;
-  cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
   cudaError_t err = cudaLaunchKernelEx(&cfg, decode_attention_kernel, p);
   B200_CHECK_ARG(err == cudaSuccess, "b200_decode_attention: launch failed: %s", cudaGetErrorString(err));
   B200_CHECK_LAUNCH("decode_attention");
@@ -434,7 +460,9 @@ extern "C" int b200_decode_embed(const long long* ids, long long ld_ids, const i
                                  const float* pos_emb, float* x, int B, int D, int pos_offset, float scale, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(ids && pos && tok_emb && pos_emb && x && B > 0 && D % 4 == 0, "b200_decode_embed: bad arguments");
-  decode_embed_kernel<<<(B * D / 4 + 255) / 256, 256, 0, s>>>(ids, ld_ids, pos, tok_emb, pos_emb, x, B, D, pos_offset, scale);
+  cudaError_t err = launch_kernel(decode_embed_kernel, dim3((B * D / 4 + 255) / 256), dim3(256), 0, s, 1, ids, ld_ids, pos,
+                                  tok_emb, pos_emb, x, B, D, pos_offset, scale);
+  B200_CHECK_ARG(err == cudaSuccess, "b200_decode_embed: launch failed: %s", cudaGetErrorString(err));
   B200_CHECK_LAUNCH("decode_embed");
   return 0;
 }
@@ -444,8 +472,10 @@ extern "C" int b200_decode_finalize(const void* argmax_partial, int n_cta, long 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(argmax_partial && ids && state && finished && B > 0 && B <= DL_M && n_cta > 0,
                  "b200_decode_finalize: bad arguments");
-  decode_finalize_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const unsigned long long*>(argmax_partial), n_cta, ids, ld_ids,
-                                            state, finished, B, eos_id);
+  cudaError_t err = launch_kernel(decode_finalize_kernel, dim3(1), dim3(1024), 0, s, 1,
+                                  reinterpret_cast<const unsigned long long*>(argmax_partial), n_cta, ids, ld_ids, state,
+                                  finished, B, eos_id);
+  B200_CHECK_ARG(err == cudaSuccess, "b200_decode_finalize: launch failed: %s", cudaGetErrorString(err));
   B200_CHECK_LAUNCH("decode_finalize");
   return 0;
 }

@@ -44,7 +44,10 @@ int num_sms() {
   return cached;
 }
 
+static int g_pdl_override = -1;      // -1: follow PIXPARSE_B200_PDL; 0 / 1: forced by b200_set_pdl()
+
 bool pdl_enabled() {
+  if (g_pdl_override >= 0) return g_pdl_override != 0;
   static int cached = -1;
   if (cached < 0) {
     const char* env = getenv("PIXPARSE_B200_PDL");
@@ -55,6 +58,19 @@ bool pdl_enabled() {
   }
   return cached != 0;
 }
+
+}  // namespace b200
+
+// The greedy-decode step is the opposite regime (pixparse_b200/decode.py): ~70 dependent kernels of a few microseconds each,
+// most of them streaming weights that do NOT depend on the predecessor -- there a dependent grid that is resident early
+// has its weight loads in flight while the predecessor drains. The host switches PDL on around the capture of that step.
+extern "C" int b200_set_pdl(int mode) {
+  const int prev = b200::g_pdl_override;
+  b200::g_pdl_override = mode < 0 ? -1 : (mode != 0);
+  return prev;
+}
+
+namespace b200 {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

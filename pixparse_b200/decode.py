@@ -11,6 +11,8 @@ Same arithmetic contract as the teacher-forced path it replaces (bf16 operands, 
 attention / GELU outputs, fp32 residual stream, logits rounded to bf16 before the argmax); decoder self-attention hides
 keys whose token is the pad id (attention_mask = input_ids.ne(pad), models/text_decoder_hf.py:68).
 """
+import os
+
 import torch
 
 from . import _lib, ops
@@ -55,9 +57,19 @@ class GreedyDecodeSession:
         self.kernels_per_step = 0
         self.eos_id = None
         self.pad_id = None
+        self.pdl = os.environ.get("PIXPARSE_B200_DECODE_PDL", "1") != "0"
 
     # ---- one decode step (enqueue only; every per-step quantity is read from device memory) -------------------------
     def _step(self):
+        # programmatic dependent launch for the whole step: each kernel's grid becomes resident while its predecessor
+        # drains, and the linears issue their (predecessor-independent) weight loads before the grid-dependency wait
+        prev = _lib.lib().b200_set_pdl(1 if self.pdl else 0)
+        try:
+            return self._enqueue_step()
+        finally:
+            _lib.lib().b200_set_pdl(prev)
+
+    def _enqueue_step(self):
         ar, B, D, H, S = self.arena, self.B, self.D, self.H, self.S
         eps = 1e-5
         n0 = _lib.launch_count()
