@@ -415,11 +415,12 @@ def extra_train_line(cfgname, env, steps, warmup, peaks):
     return out
 
 
-def eval_ocr_line(env, batch=None, new_tokens=None, uncached_tokens=24):
+def eval_ocr_line(env, batch=None, new_tokens=None, uncached_tokens=24, stock_reference=True):
     """BASELINE configs[4]: encoder once, then greedy decode of a FIXED number of tokens (random weights do not emit EOS
     reliably) through TaskCrullerEvalOCR's model + ocr_utils.get_generated_tokens(use_cache=True). The
     reference's own loop (whole prefix re-fed every step, ocr_utils.py:182-196) is timed beside it on a short prefix."""
     from pixparse_b200 import _lib, synthetic
+    from pixparse_b200.engine import engine_for
     from pixparse_b200.ocr_utils import get_generated_tokens
     from pixparse_b200.task_eval_ocr import TaskCrullerEvalOCR, TaskCrullerEvalOCRCfg
     c = CONFIGS["eval_ocr"]
@@ -463,27 +464,87 @@ def eval_ocr_line(env, batch=None, new_tokens=None, uncached_tokens=24):
         assert ids_host.shape == (B, tokens + 1), ids_host.shape
         return ms_enc, ms_all
 
+    sampler = ClockSampler(dev.index if dev.index is not None else 0)
+    sampler.start()
     _lib.reset_launch_count()
     ms_enc, ms_all = timed(T, True, reps=2)
     launches = _lib.launch_count() // 2
+    sampler.stop()
     ms_dec = ms_all - ms_enc
     _, ms_unc = timed(uncached_tokens, False, reps=1)
     _, ms_c_short = timed(uncached_tokens, True, reps=1)
+    # HBM roofline of one token step: every decoder weight once (bf16), the cross-attention K | V of the image tokens,
+    # the self-attention K | V of the prefix (average length T / 2); activations for 16 pages are noise next to these
+    ar = engine_for(task.model.text_decoder).arena
+    dcfg = task.model.text_decoder.trunk.config
+    D, nl, S = dcfg.d_model, dcfg.decoder_layers, enc_tokens(size, task.model)
+    w_bytes = 2 * (ar.index["dec.tok"][1] + sum(ar.index[k][1] for k in ar.keys if k.startswith("dec.") and k.endswith(".w")
+                                                and ".ca.k." not in k and ".ca.v." not in k and "ln" not in k))
+    kv_bytes = nl * B * (S + T / 2) * 2 * D * 2
+    step_bytes = w_bytes + kv_bytes
+    peaks = load_peaks()
+    ref = None
+    if stock_reference:
+        try:
+            ref = time_gpu_reference_decode(c["model"], B, uncached_tokens, dev)
+        except Exception as e:      # the reference arm must never take the repo's line down
+            ref = {"unavailable": repr(e)[:200]}
     out = {"metric": "cruller_large_6layers eval_ocr greedy decode tokens/sec", "value": B * T / (ms_dec * 1e-3),
            "unit": "tokens/s", "pages_per_s": B / (ms_all * 1e-3), "ms_encoder": ms_enc, "ms_decode": ms_dec,
            "ms_per_token_step": ms_dec / T, "n_gpus": 1,
            "config": {"workload": c["workload"].format(B=B, T=T), "batch": B, "new_tokens": T, "kv_cache": True,
-                      "note": "timed end to end: pinned host pages -> H2D -> encoder -> decode loop -> ids back on the host"},
+                      "note": "timed end to end: pinned host pages -> H2D -> encoder -> decode loop -> ids back on the host; "
+                              "the decode loop is one CUDA graph of single-token kernels replayed per token"},
            "e2e": {"value": B * T / (ms_all * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": host_img.numel() * 4,
                    "d2h_bytes_per_step": B * (T + 1) * 8},
+           "roofline": {"bound": "hbm", "kernel": "decode step (decode_linear / decode_attention / layernorm, 77 kernels)",
+                        "achieved": step_bytes / (ms_dec / T * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": step_bytes / (ms_dec / T * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                        "bytes_per_token_step": int(step_bytes), "weight_bytes": int(w_bytes), "kv_bytes": int(kv_bytes),
+                        "per_kernel": "profiles/r02_ncu_hbm_kernels.txt (decode_attention 4.9 TB/s, LM head 3.1 TB/s)"},
            "uncached_reference_loop": {"new_tokens": uncached_tokens, "ms": ms_unc - ms_enc,
                                        "kv_cached_same_tokens_ms": ms_c_short - ms_enc,
                                        "what": "ocr_utils.py:182-196 as written (whole prefix re-fed each step) on this repo's "
                                                "kernels"},
+           "gpu_reference": ref, "clocks": sampler.summary(),
            "gpu_launches": launches, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    if ref and "ms" in ref:
+        # per generated token: the reference loop's cost grows with the prefix, so this ratio (taken over its first
+        # `uncached_tokens` tokens, its cheapest) is a lower bound for longer outputs
+        out["gpu_reference"]["ratio_b200_over_stock_torch"] = (ref["ms"] / max(ref["new_tokens"], 1)) / (ms_dec / T)
     del task
     release({})
     return out
+
+
+def enc_tokens(size, model):
+    p = model.image_encoder.trunk.arch['patch_size']
+    return (size[0] // p) * (size[1] // p) + 1
+
+
+def time_gpu_reference_decode(model_name, B, tokens, dev):
+    """The reference's own greedy loop (utils/ocr_utils.py:165-197: whole prefix re-fed each step, no KV cache) on stock
+    PyTorch: oracle modules under torch.autocast(bf16) on the same GPU. Only this reference leg touches oracle/."""
+    from oracle import cruller_ref
+    from pixparse_b200 import synthetic
+    model = cruller_ref.build_model(model_name, vocab_size=synthetic.PRETRAIN_VOCAB, seed=0).to(dev).eval()
+    size = tuple(cruller_ref.MODEL_CONFIGS[model_name].image_encoder.image_size)
+    img = torch.rand((B, 1) + size, device=dev)
+    with torch.inference_mode(), torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+        enc = torch.cat([model.image_encoder(img[i:i + 4]) for i in range(0, B, 4)])
+        cruller_ref.greedy_decode_uncached(model, enc, synthetic.S_PRETRAIN_ID, 1, 2, 4)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ids = cruller_ref.greedy_decode_uncached(model, enc, synthetic.S_PRETRAIN_ID, 1, 2, tokens)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tokens = ids.shape[1] - 1
+    del model
+    torch.cuda.empty_cache()
+    return {"ms": ms, "new_tokens": tokens, "tokens_per_s": B * tokens / (ms * 1e-3),
+            "what": "oracle modules (transformers BartForCausalLM) under torch.autocast(bf16), the reference's uncached loop"}
 
 
 def hbm_roofline(task, B, peaks):
