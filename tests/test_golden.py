@@ -21,7 +21,7 @@ def _case_to_model(case):
             "vit_base_patch16_224": "cruller_base"}[enc]
 
 
-@pytest.mark.parametrize("name", ["pretrain_tiny", "pretrain_tiny_prenorm"])
+@pytest.mark.parametrize("name", ["pretrain_tiny", "pretrain_tiny_prenorm", "pretrain_cruller_base_b2"])
 def test_oracle_reproduces_reference_train_steps(name):
     """Same seed -> same init -> the restated train step must reproduce the reference's loss / grad-norm / lr /
     logits for several optimizer updates (fp32 CPU; tolerance covers thread-count dependent summation order)."""

@@ -53,6 +53,51 @@ def test_vit_restatement_matches_independent_hf_vit():
     assert torch.allclose(y_ours, y_hf, atol=2e-5, rtol=1e-4)
 
 
+def test_prenorm_vit_restatement_matches_independent_hf_clip_vision():
+    """The pre-norm (CLIP-style: no patch bias, LayerNorm before the blocks) variant of the restatement -- the
+    cruller_large encoder -- against transformers.CLIPVisionModel with hidden_act='gelu' (separate code, separate q / k / v
+    projections). CLIP's vision tower normalises only the pooled token at the end; timm's forward_features normalises every
+    token, so HF's post_layernorm is applied to all of last_hidden_state here."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    torch.manual_seed(0)
+    ours = vit_timm.create_model("vit_test_patch14_clip", in_chans=3, img_size=(56, 56)).eval()
+    a = ours.arch
+    assert a["pre_norm"]
+    D = a["embed_dim"]
+    cfg = CLIPVisionConfig(hidden_size=D, intermediate_size=int(D * a["mlp_ratio"]), num_hidden_layers=a["depth"],
+                           num_attention_heads=a["num_heads"], num_channels=3, image_size=56, patch_size=a["patch_size"],
+                           hidden_act="gelu", layer_norm_eps=a["ln_eps"], attention_dropout=0.0)
+    hf = CLIPVisionModel(cfg).eval()
+    sd = ours.state_dict()
+    assert "patch_embed.proj.bias" not in sd
+    new = {"embeddings.class_embedding": sd["cls_token"].reshape(D), "embeddings.position_embedding.weight": sd["pos_embed"][0],
+           "embeddings.patch_embedding.weight": sd["patch_embed.proj.weight"],
+           "pre_layrnorm.weight": sd["norm_pre.weight"], "pre_layrnorm.bias": sd["norm_pre.bias"],
+           "post_layernorm.weight": sd["norm.weight"], "post_layernorm.bias": sd["norm.bias"]}
+    for i in range(a["depth"]):
+        p, q = f"blocks.{i}.", f"encoder.layers.{i}."
+        w, b = sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]
+        for n, name in enumerate(("q_proj", "k_proj", "v_proj")):
+            new[q + f"self_attn.{name}.weight"] = w[n * D:(n + 1) * D]
+            new[q + f"self_attn.{name}.bias"] = b[n * D:(n + 1) * D]
+        new[q + "self_attn.out_proj.weight"] = sd[p + "attn.proj.weight"]
+        new[q + "self_attn.out_proj.bias"] = sd[p + "attn.proj.bias"]
+        new[q + "layer_norm1.weight"], new[q + "layer_norm1.bias"] = sd[p + "norm1.weight"], sd[p + "norm1.bias"]
+        new[q + "layer_norm2.weight"], new[q + "layer_norm2.bias"] = sd[p + "norm2.weight"], sd[p + "norm2.bias"]
+        new[q + "mlp.fc1.weight"], new[q + "mlp.fc1.bias"] = sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]
+        new[q + "mlp.fc2.weight"], new[q + "mlp.fc2.bias"] = sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"]
+    vm = hf.vision_model
+    missing, unexpected = vm.load_state_dict(new, strict=False)
+    missing = [m for m in missing if "position_ids" not in m]
+    assert not unexpected and not missing, (missing, unexpected)
+    x = torch.randn(2, 3, 56, 56)
+    with torch.no_grad():
+        y_ours = ours(x)
+        y_hf = vm.post_layernorm(vm(pixel_values=x).last_hidden_state)
+    assert y_ours.shape == (2, 17, D)
+    assert torch.allclose(y_ours, y_hf, atol=2e-5, rtol=1e-4)
+
+
 def test_oracle_shapes_and_param_counts():
     m = cruller_ref.build_model("cruller_test", vocab_size=50267, seed=0)
     img = torch.randn(2, 1, 64, 48)
