@@ -141,6 +141,182 @@ ce_fwd_bwd_kernel(const bf16* __restrict__ logits, long long ld, const long long
   }
 }
 
+// Persistent, software-pipelined form of the kernel above (used whenever two rows fit in shared memory, i.e. always for
+// the BART vocabularies): one CTA per SM loops over rows; a producer thread moves whole rows with 1-D bulk copies --
+// global -> shared on an mbarrier, shared -> global as bulk-group stores -- so the load of row i + 1 and the store of row
+// i - 1 are in flight while the 31 compute warps make their three passes over row i. The one-CTA-per-row kernel keeps
+// its load, compute and store phases apart (two co-resident CTAs only partly overlap them: 4.4 TB/s, ncu
+// profiles/r02_ncu_hbm_kernels.txt); here HBM sees a continuous read and a continuous write stream.
+constexpr int CEP_WARPS = 31;                  // compute warps; warp 31 is the producer
+constexpr int CEP_COMPUTE = CEP_WARPS * 32;
+
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ float cep_reduce(float v, float* red, bool is_max) {      // over the 992 compute threads
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = v;
+  named_bar_sync(1, CEP_COMPUTE);
+  float r = lane < CEP_WARPS ? red[lane] : (is_max ? -INFINITY : 0.f);
+  r = is_max ? warp_max(r) : warp_sum(r);
+  named_bar_sync(1, CEP_COMPUTE);
+  return r;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+ce_fwd_bwd_pipe_kernel(const bf16* __restrict__ logits, long long ld, const long long* __restrict__ targets,
+                       bf16* __restrict__ dlogits, long long ldd, float* __restrict__ row_loss, float* __restrict__ stats,
+                       int rows, int V, long long ignore_index, float grad_scale) {
+  extern __shared__ uint4 ce_smem[];
+  __shared__ uint64_t full_bar[2], done_bar[2];
+  __shared__ float red[32];
+  __shared__ float s_xt;
+  const int nvec = (V + 7) / 8;
+  const uint32_t row_bytes = (uint32_t)nvec * 16u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+    mbar_init(&done_bar[0], CEP_WARPS); mbar_init(&done_bar[1], CEP_WARPS);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int stride = gridDim.x;
+  if (warp == CEP_WARPS) {
+    if (lane != 0) return;
+    for (int it = 0; it < 2; ++it) {
+      const long long row = blockIdx.x + (long long)it * stride;
+      if (row < rows) {
+        mbar_expect_tx(&full_bar[it], row_bytes);
+        bulk_load_1d(ce_smem + (size_t)it * nvec, logits + row * ld, row_bytes, &full_bar[it]);
+      }
+    }
+    for (int it = 0;; ++it) {
+      const long long row = blockIdx.x + (long long)it * stride;
+      if (row >= rows) break;
+      const int b = it & 1;
+      mbar_wait(&done_bar[b], (it >> 1) & 1);      // the gradient of row `it` is in buffer b (writers fenced to the async proxy)
+      if (dlogits != nullptr) {
+        bulk_store_1d(dlogits + row * ldd, ce_smem + (size_t)b * nvec, row_bytes);
+        tma_commit_group();
+      }
+      const long long next = row + 2LL * stride;
+      if (next < rows) {
+        if (dlogits != nullptr) tma_wait_group_read<0>();      // the store has read buffer b
+        mbar_expect_tx(&full_bar[b], row_bytes);
+        bulk_load_1d(ce_smem + (size_t)b * nvec, logits + next * ld, row_bytes, &full_bar[b]);
+      }
+    }
+    if (dlogits != nullptr) tma_wait_group<0>();
+    return;
+  }
+  const float kLog2e = 1.4426950408889634f;
+  const float n_valid = stats[0];
+  const float inv_n = n_valid > 0.f ? 1.0f / n_valid : 0.f;
+  const float gs = grad_scale * inv_n;
+  for (int it = 0;; ++it) {
+    const long long row = blockIdx.x + (long long)it * stride;
+    if (row >= rows) break;
+    const int b = it & 1;
+    uint4* buf = ce_smem + (size_t)b * nvec;
+    const long long tgt = targets[row];
+    mbar_wait(&full_bar[b], (it >> 1) & 1);
+    if (tgt == ignore_index) {
+      if (dlogits != nullptr)
+        for (int i = threadIdx.x; i < nvec; i += CEP_COMPUTE) buf[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_loss && threadIdx.x == 0) row_loss[row] = 0.f;
+    } else {
+      // The kernel is bound by instruction issue (ncu: 62 % of the issue slots, eligible warps waiting to be selected), so
+      // the three passes over the staged row are written for instruction count: four vectors per trip (predicated, four
+      // shared-memory loads in flight), the row maximum with packed bf16 max, exp / scale arithmetic on packed fp32 pairs.
+      const int tvec = (int)(tgt >> 3), te = (int)(tgt & 7);
+      if (threadIdx.x == 0) s_xt = __bfloat162float(reinterpret_cast<const bf16*>(buf + tvec)[te]);      // before anything is rewritten
+      if ((V & 7) && threadIdx.x == 32) {      // padding columns of the last vector -> -inf (bf16 0xff80)
+        uint4 v = buf[nvec - 1];
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int e = (V & 7); e < 8; ++e) {
+          const int wi = e >> 1;
+          w[wi] = (e & 1) ? ((w[wi] & 0x0000ffffu) | 0xff800000u) : ((w[wi] & 0xffff0000u) | 0x0000ff80u);
+        }
+        buf[nvec - 1] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      named_bar_sync(1, CEP_COMPUTE);
+      __nv_bfloat162 m2 = __float2bfloat162_rn(-INFINITY);
+      for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * CEP_COMPUTE) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * CEP_COMPUTE;
+          if (i < nvec) {
+            const uint4 v = buf[i];
+            m2 = __hmax2(m2, __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v.x), *reinterpret_cast<const __nv_bfloat162*>(&v.y)),
+                                     __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v.z), *reinterpret_cast<const __nv_bfloat162*>(&v.w))));
+          }
+        }
+      }
+      float mx = fmaxf(__bfloat162float(m2.x), __bfloat162float(m2.y));
+      mx = cep_reduce(mx, red, true);
+      const f32x2 k2 = f2_splat(kLog2e), mneg2 = f2_splat(-mx * kLog2e);
+      f32x2 sum2 = f2_splat(0.f);
+      for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * CEP_COMPUTE) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * CEP_COMPUTE;
+          if (i < nvec) {
+            const uint4 v = buf[i];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a0, a1;
+              f2_unpack(f2_fma(f2_pack(bf16_lo(w[q]), bf16_hi(w[q])), k2, mneg2), a0, a1);
+              const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
+              sum2 = f2_add(sum2, f2_pack(e0, e1));
+              o[q] = pack_bf16(e0, e1);
+            }
+            if (dlogits != nullptr) buf[i] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      float s_lo, s_hi;
+      f2_unpack(sum2, s_lo, s_hi);
+      const float sum = cep_reduce(s_lo + s_hi, red, false);      // (its barriers also publish the rewritten row)
+      if (threadIdx.x == 0) {
+        const float l = logf(sum) + mx - s_xt;
+        if (row_loss) row_loss[row] = l;
+        atomicAdd(stats + 1, l * inv_n);
+      }
+      if (dlogits != nullptr) {
+        const float c = gs / sum;
+        const f32x2 c2 = f2_splat(c);
+        for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * CEP_COMPUTE) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * CEP_COMPUTE;
+            if (i < nvec) {
+              const uint4 v = buf[i];
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+              float p[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) f2_unpack(f2_mul(f2_pack(bf16_lo(w[q]), bf16_hi(w[q])), c2), p[2 * q], p[2 * q + 1]);
+              if (i == tvec) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (e == te) p[e] -= gs;
+              }
+              buf[i] = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+            }
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();      // this thread's writes to buffer b -> visible to the bulk store
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done_bar[b]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // global grad norm (deterministic two-stage) + fused AdamW
 // ------------------------------------------------------------------------------------------------
@@ -277,6 +453,25 @@ extern "C" int b200_ce_fwd_bwd(const void* logits_bf16, long long ld, const long
   if (dlogits_bf16) B200_CHECK_ARG(ldd % 8 == 0 && ldd >= (vocab + 7) / 8 * 8, "b200_ce_fwd_bwd: bad ldd");
   const int smem = (vocab + 7) / 8 * 16;
   B200_CHECK_ARG(smem <= 200 * 1024, "b200_ce_fwd_bwd: vocab %d too large for the single-pass kernel", vocab);
+  static int pipe_mode = -1;      // PIXPARSE_B200_CE_PIPE=0: the one-CTA-per-row kernel (A/B)
+  if (pipe_mode < 0) {
+    const char* env = getenv("PIXPARSE_B200_CE_PIPE");
+    pipe_mode = (env != nullptr && env[0] == '0') ? 0 : 1;
+  }
+  if (pipe_mode == 1 && 2 * smem <= 220 * 1024) {
+    static int configured_pipe = 0;
+    if (2 * smem > configured_pipe) {
+      cudaError_t e = cudaFuncSetAttribute(ce_fwd_bwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * smem);
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ce pipe)");
+      configured_pipe = 2 * smem;
+    }
+    const int grid = rows < num_sms() ? rows : num_sms();
+    ce_fwd_bwd_pipe_kernel<<<grid, 1024, 2 * smem, s>>>(reinterpret_cast<const bf16*>(logits_bf16), ld, targets,
+                                                        reinterpret_cast<bf16*>(dlogits_bf16), ldd, row_loss, stats, rows,
+                                                        vocab, ignore_index, grad_scale);
+    B200_CHECK_LAUNCH("ce_fwd_bwd_pipe");
+    return 0;
+  }
   static int configured_smem = 0;
   if (smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(ce_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
