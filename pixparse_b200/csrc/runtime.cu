@@ -51,7 +51,7 @@ bool pdl_enabled() {
   static int cached = -1;
   if (cached < 0) {
     const char* env = getenv("PIXPARSE_B200_PDL");
-    // opt-in: measured on B200 (profiles/r02_pdl_ab.txt) the step is 0.5-1 % SLOWER with it -- the kernels here own whole
+    // opt-in: measured on B200 (profiles/r02_experiments_no_gain.txt) the step is 0.5-1 % SLOWER with it -- the kernels here own whole
     // SMs, so a dependent CTA cannot become resident before its predecessor's CTA has left, and the front end already
     // hides the launch latency of a queued kernel
     cached = (env != nullptr && env[0] == '1') ? 1 : 0;
