@@ -84,15 +84,35 @@ def test_b200_train_steps_match_reference_golden(cuda_lib, name):
                                 num_intervals=o["num_intervals"], updates_per_interval=o["steps_per_interval"])
     sched.step_update(0)
     eng.zero_grads()
+    # the oracle's train step in fp32 on the same GPU, side by side: it reproduces the golden numbers (checked on CPU in
+    # test_oracle_reproduces_reference_train_steps) and gives the parameter values after each update
+    ref = ref.cuda()
+    tr = cruller_ref.OracleTrainer(ref, g["vocab"], lr=o["lr"], betas=tuple(o["betas"]), eps=o["eps"],
+                                   clip_grad=o["clip_grad"], num_intervals=o["num_intervals"],
+                                   num_warmup_intervals=o["num_warmup_intervals"],
+                                   steps_per_interval=o["steps_per_interval"])
+    lr_sum = 0.0
     for step, refstep in enumerate(g["steps"]):
         image, text, target = synthetic.synthetic_batch(c["B"], tuple(c["size"]), c["Lt"], seed=g["seed"] + step)
+        lr_sum += max(pg["lr"] for pg in opt.param_groups)
         stats = eng.forward_backward(image.cuda(), text[:, :-1].contiguous().cuda(), target[:, 1:].contiguous().cuda())
         opt.step(clip_grad_norm=o["clip_grad"])
         sched.step_update(step + 1)
+        out = tr.train_step((image.cuda(), text.cuda(), target.cuda()))
+        assert out["loss"] == pytest.approx(refstep["loss"], rel=2e-5)      # fp32 oracle on the GPU == golden
         assert stats[1].item() == pytest.approx(refstep["loss"], rel=1e-3)
         assert opt.norm_stats[1].item() == pytest.approx(refstep["grad_norm"], rel=2e-2)
         lr = sum(pg["lr"] for pg in opt.param_groups) / len(opt.param_groups)
         assert lr == pytest.approx(refstep["lr_after"], rel=1e-9, abs=1e-15)
+    # parameters after the updates: an AdamW step moves a weight by at most ~lr, so bf16 gradient noise can
+    # separate the two runs by at most 2 * lr per update, wherever the gradient's sign is in doubt
+    ref_params = dict(ref.named_parameters())
+    worst = max((p.detach().float() - ref_params[n].detach().float()).abs().max().item() for n, p in ours.named_parameters())
+    assert worst <= 2.0 * lr_sum + 1e-7, (worst, lr_sum)
+    moved = sum(((p.detach().float() - ref_params[n].detach().float()).abs() > 0.5 * lr_sum).float().sum().item()
+                for n, p in ours.named_parameters())
+    total = sum(p.numel() for p in ours.parameters())
+    assert moved <= 0.05 * total, f"{moved} of {total} weights differ from the fp32 oracle by more than half an update"
 
 
 def test_annotation_preprocessors_match_reference_golden():
