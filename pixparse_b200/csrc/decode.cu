@@ -229,12 +229,16 @@ decode_linear_kernel(const DecodeLinearParams p) {
   }
 }
 
-// groups of 8 weight rows per CTA: as many as still leave >= 2 CTAs per SM (small layers run at G = 1: 128 CTAs for N = 1024)
+// groups of 8 weight rows per CTA: 2 when that still leaves >= 2 CTAs per SM (the LM head: 3142 CTAs, three resident per SM;
+// measured 34 us against 39 us at G = 4 and 44 us at G = 1), else 1 (128 CTAs for N = 1024). PIXPARSE_B200_DECODE_G overrides.
 static int decode_linear_groups(int n) {
-  const int want = 2 * num_sms();
-  if ((n + 31) / 32 >= want) return 4;
-  if ((n + 15) / 16 >= want) return 2;
-  return 1;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* env = getenv("PIXPARSE_B200_DECODE_G");
+    forced = env != nullptr ? atoi(env) : 0;
+  }
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
+  return (n + 15) / 16 >= 2 * num_sms() ? 2 : 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,8 +271,8 @@ decode_attention_kernel(const DecodeAttnParams p) {
   pdl_launch_dependents();      // the next linear may start pulling its weights
   pdl_wait();                   // q (and the position) come from the predecessors
   const int Sk = p.pos != nullptr ? *p.pos + 1 : p.sk;
-  const int nblk = (Sk + 31) >> 5, per = (nblk + nsplit - 1) / nsplit;
-  const int blk0 = split * per, blk1 = min(nblk, blk0 + per);
+  const int nblk = (Sk + 31) >> 5;      // balanced partition of the 32-key blocks over the splits
+  const int blk0 = (int)(((long long)nblk * split) / nsplit), blk1 = (int)(((long long)nblk * (split + 1)) / nsplit);
   // this lane's 8 dims of the query, pre-multiplied by scale * log2(e)
   f32x2 q0, q1, q2, q3;
   {
@@ -507,12 +511,19 @@ extern "C" int b200_decode_attention(const B200DecodeAttentionArgs* a, void* str
   p.pos = a->pos; p.sk = a->sk;
   p.key_ids = a->key_ids; p.ld_ids = a->ld_ids; p.pad_id = a->pad_id;
   p.H = a->heads; p.scale_log2 = a->scale * 1.4426950408889634f;
-  // key splits: ~5 blocks of 32 keys per warp (cross-attention over the image tokens: 2509 keys -> 4 CTAs per (page, head),
-  // ~7 CTAs per SM at 16 pages x 16 heads); the growing self-attention prefix (device-side length) stays in one CTA
+  // key splits: ~10 blocks of 32 keys per warp (cross-attention over the image tokens: 2509 keys -> 2 CTAs per (page, head),
+  // 512 CTAs all resident at 16 pages x 16 heads: 38 us against 40 us with 4 splits, 44-48 us with 3 or 5-8);
+  // the growing self-attention prefix (device-side length) stays in one CTA
   int nsplit = 1;
   if (a->pos == nullptr) {
     const int nblk = (a->sk + 31) / 32;
-    nsplit = (nblk + DA_WARPS * 5 - 1) / (DA_WARPS * 5);
+    nsplit = (nblk + DA_WARPS * 10 - 1) / (DA_WARPS * 10);
+    static int forced = -1;      // PIXPARSE_B200_DECODE_SPLITS=<n>: experiments
+    if (forced < 0) {
+      const char* env = getenv("PIXPARSE_B200_DECODE_SPLITS");
+      forced = env != nullptr ? atoi(env) : 0;
+    }
+    if (forced > 0) nsplit = forced;
     nsplit = nsplit < 1 ? 1 : (nsplit > DA_MAX_SPLITS ? DA_MAX_SPLITS : nsplit);
   }
   cudaLaunchConfig_t cfg = {};
