@@ -285,17 +285,33 @@ decode_attention_kernel(const DecodeAttnParams p) {
   const bf16* vbase = p.v + (long long)b * p.kv_bstride + p.v_col0 + h * 64 + 8 * c;
   float m_run = -INFINITY, l_run = 0.f;
   f32x2 a0 = f2_splat(0.f), a1 = f2_splat(0.f), a2 = f2_splat(0.f), a3 = f2_splat(0.f);      // dims 8 c .. 8 c + 7 (this group's keys)
-  for (int blk = blk0 + warp; blk < blk1; blk += DA_WARPS) {
-    const int kb = blk << 5;
-    uint4 kk[8], vv[8];
+  // Software pipeline: the K rows of the NEXT block are requested as soon as this block's scores are done (their registers are
+  // free), its V rows as soon as this block's P V is done -- every warp keeps 8 + 8 16-byte loads in flight while it computes,
+  // instead of alternating between a load phase and a compute phase.
+  uint4 kk[8], vv[8];
+  auto load_k = [&](int kb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       // unconditional loads (keys past the end re-read the last key: its score is masked below, so its V row, which is
-      // finite, is weighted by 0): unpredicated loads are hoisted together, all 16 of a block are in flight at once
+      // finite, is weighted by 0): unpredicated loads are issued together
       const int key = min(kb + 4 * i + g, Sk - 1);
       kk[i] = ld_nc_na(reinterpret_cast<const uint4*>(kbase + (long long)key * p.ld_kv));
+    }
+  };
+  auto load_v = [&](int kb) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = min(kb + 4 * i + g, Sk - 1);
       vv[i] = ld_nc_na(reinterpret_cast<const uint4*>(vbase + (long long)key * p.ld_kv));
     }
+  };
+  if (blk0 + warp < blk1) {
+    load_k((blk0 + warp) << 5);
+    load_v((blk0 + warp) << 5);
+  }
+  for (int blk = blk0 + warp; blk < blk1; blk += DA_WARPS) {
+    const int kb = blk << 5;
+    const bool has_next = blk + DA_WARPS < blk1;      // (warp-uniform)
     const int my_key = kb + 4 * c + g;
     bool valid = my_key < Sk;
     if (valid && p.key_ids != nullptr) valid = p.key_ids[(long long)b * p.ld_ids + my_key] != p.pad_id;
@@ -314,8 +330,8 @@ decode_attention_kernel(const DecodeAttnParams p) {
       r += __shfl_xor_sync(0xffffffffu, r, 4);
       if (i == c && valid) s = r;
     }
-    // (no early-out for a fully hidden block: a branch here makes the V loads conditional and the compiler sinks them below
-    // the softmax, one more serialised DRAM round trip per block)
+    if (has_next) load_k((blk + DA_WARPS) << 5);
+    // (no early-out for a fully hidden block: everything below is branch-free arithmetic)
     const float m_new = fmaxf(m_run, warp_max(s));
     const float pr = valid ? ex2_approx(s - m_new) : 0.f;
     const float alpha = m_new == -INFINITY ? 1.f : ex2_approx(m_run - m_new);      // 0 on the first visible block (m_run = -inf)
@@ -331,6 +347,7 @@ decode_attention_kernel(const DecodeAttnParams p) {
       a2 = f2_fma(pj, f2_pack(bf16_lo(vv[i].z), bf16_hi(vv[i].z)), a2);
       a3 = f2_fma(pj, f2_pack(bf16_lo(vv[i].w), bf16_hi(vv[i].w)), a3);
     }
+    if (has_next) load_v((blk + DA_WARPS) << 5);
     m_run = m_new;
   }
   // sum the four key groups of the warp, then the warps of the CTA, then the CTAs of the cluster
