@@ -299,8 +299,7 @@ int b200_adamw_step(const B200AdamWArgs* args, void* stream);
  *   outputs bf16 and/or fp32 with row pitch ldo, shifted by (*pos) * out_pos_stride elements when pos != NULL (appending
  *   K | V to a [B, T_max, 2D] cache). With out2_bf16 the output is split at column n_split: [0, n_split) -> out_bf16 / out_f32
  *   unshifted, [n_split, N) -> out2_bf16 shifted (the packed q | k | v projection: q dense, k | v appended to the cache).
- *   With ln_gamma the rows of out_f32 are LayerNorm-ed into ln_out_* by the last CTA of the same launch (post-LN BART:
- *   every residual sum is followed by a LayerNorm). With argmax_partial != NULL nothing is stored: the per-CTA (max, argmax) of the
+ *   With argmax_partial != NULL nothing is stored: the per-CTA (max, argmax) of the
  *   bf16-rounded outputs is written as [16][b200_decode_linear_ctas(N)] packed 64-bit keys (LM head fused with argmax).
  * decode_attention: one query per (page, head): q [B, ldq], K / V rows ld_kv apart, pages kv_bstride apart; the key
  *   count is sk, or (*pos) + 1 when pos != NULL; key j of page b is hidden when key_ids[b * ld_ids + j] == pad_id
@@ -332,13 +331,6 @@ typedef struct B200DecodeLinearArgs {
   int n_split;             /* with out2_bf16: columns >= n_split go to out2 (column n - n_split) and only they are shifted */
   void* out2_bf16;
   long long ldo2;
-  const float* ln_gamma;   /* != NULL: LayerNorm(out_f32 rows) fused behind the linear (the CTA finishing last runs it) */
-  const float* ln_beta;
-  void* ln_out_bf16;       /* [M, N] dense */
-  float* ln_out_f32;       /* [M, N] dense */
-  unsigned int* ln_counter; /* one zeroed device word; left at zero */
-  float ln_eps;
-  int reserved;
 } B200DecodeLinearArgs;
 int b200_decode_linear(const B200DecodeLinearArgs* args, void* stream);
 int b200_decode_linear_ctas(int n);

@@ -110,9 +110,7 @@ class AdamWArgs(_Args):
 class DecodeLinearArgs(_Args):
     _fields_ = [("struct_size", _U), ("m", _I), ("x", _P), ("ldx", _L), ("w", _P), ("ldw", _L), ("bias", _P), ("resid", _P),
                 ("ld_resid", _L), ("out_bf16", _P), ("out_f32", _P), ("ldo", _L), ("pos", _P), ("out_pos_stride", _L),
-                ("argmax_partial", _P), ("n", _I), ("k", _I), ("act", _I), ("n_split", _I), ("out2_bf16", _P), ("ldo2", _L),
-                ("ln_gamma", _P), ("ln_beta", _P), ("ln_out_bf16", _P), ("ln_out_f32", _P), ("ln_counter", _P),
-                ("ln_eps", _F), ("reserved", _I)]
+                ("argmax_partial", _P), ("n", _I), ("k", _I), ("act", _I), ("n_split", _I), ("out2_bf16", _P), ("ldo2", _L)]
 
 
 class DecodeAttentionArgs(_Args):

@@ -45,8 +45,6 @@ struct DecodeLinearParams {
   // split output: columns >= n_split go to out2 (bf16, pitch ldo2, column n - n_split) and only THEY take the position
   // shift -- the packed q | k | v projection of a decode step writes q to a dense buffer and k | v into the cache
   int n_split; bf16* out2; long long ldo2;
-  // fused LayerNorm of the finished [M, N] fp32 output (needs out32): the CTA that finishes last normalises all rows
-  const float* ln_gamma; const float* ln_beta; float ln_eps; bf16* ln_out16; float* ln_out32; unsigned int* ln_counter;
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -165,67 +163,6 @@ decode_linear_kernel(const DecodeLinearParams p) {
     const long long sh = p.out2 != nullptr ? 0 : shift;
     if (p.out32 != nullptr) p.out32[sh + (long long)m * p.ldo + n] = v;
     if (p.out16 != nullptr) p.out16[sh + (long long)m * p.ldo + n] = __float2bfloat16_rn(v);
-  }
-  if (p.ln_counter == nullptr) return;
-  // ---- fused LayerNorm: the last CTA to get here sees every CTA's slice of out32 (threadfence + ticket) ----------------
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int ticket = atomicAdd(p.ln_counter, 1u);
-    s_last = ticket == gridDim.x - 1;
-    if (s_last) *p.ln_counter = 0u;      // ready for the next launch (stream order)
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // one warp per row pair (m, m + 8), rows held in registers (N <= 1024: 8 float4 per lane and row), both rows' loads in
-  // flight together: one L2 round trip, then shuffles
-  constexpr int LNV = 8;
-  const float inv_n = 1.0f / (float)p.N;
-  float4 v[2][LNV];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int m = min(warp + 8 * r, p.M - 1);
-    const float* row = p.out32 + (long long)m * p.ldo;
-#pragma unroll
-    for (int i = 0; i < LNV; ++i) {
-      const int n = (lane + 32 * i) * 4;
-      v[r][i] = n < p.N ? __ldcg(reinterpret_cast<const float4*>(row + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int m = warp + 8 * r;
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < LNV; ++i) sum += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-    const float mean = warp_sum(sum) * inv_n;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < LNV; ++i) {
-      if ((lane + 32 * i) * 4 < p.N) {
-        const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
-        q += (a * a + b * b) + (c * c + d * d);
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(q) * inv_n + p.ln_eps);
-    if (m >= p.M) continue;      // (warp-uniform)
-#pragma unroll
-    for (int i = 0; i < LNV; ++i) {
-      const int n = (lane + 32 * i) * 4;
-      if (n >= p.N) continue;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + n));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.ln_beta + n));
-      float4 o;
-      o.x = (v[r][i].x - mean) * rstd * g.x + b.x;
-      o.y = (v[r][i].y - mean) * rstd * g.y + b.y;
-      o.z = (v[r][i].z - mean) * rstd * g.z + b.z;
-      o.w = (v[r][i].w - mean) * rstd * g.w + b.w;
-      if (p.ln_out32 != nullptr) *reinterpret_cast<float4*>(p.ln_out32 + (long long)m * p.N + n) = o;
-      if (p.ln_out16 != nullptr)
-        *reinterpret_cast<uint2*>(p.ln_out16 + (long long)m * p.N + n) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
-    }
   }
 }
 
@@ -485,16 +422,8 @@ extern "C" int b200_decode_linear(const B200DecodeLinearArgs* a, void* stream) {
   p.argmax_partial = reinterpret_cast<unsigned long long*>(a->argmax_partial);
   p.M = a->m; p.N = a->n; p.K = a->k; p.act = a->act;
   p.n_split = a->n_split; p.out2 = reinterpret_cast<bf16*>(a->out2_bf16); p.ldo2 = a->ldo2;
-  p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps;
-  p.ln_out16 = reinterpret_cast<bf16*>(a->ln_out_bf16); p.ln_out32 = a->ln_out_f32;
-  p.ln_counter = a->ln_gamma != nullptr ? a->ln_counter : nullptr;
   B200_CHECK_ARG(a->out2_bf16 == nullptr || (a->n_split > 0 && a->n_split < a->n && a->argmax_partial == nullptr),
                  "b200_decode_linear: split output needs 0 < n_split < n");
-  B200_CHECK_ARG(a->ln_gamma == nullptr || (a->ln_beta && a->ln_counter && a->out_f32 && a->n % 4 == 0 && a->n <= 1024 && a->ldo % 4 == 0 &&
-                                            a->pos == nullptr && a->out2_bf16 == nullptr && a->argmax_partial == nullptr &&
-                                            (a->ln_out_bf16 || a->ln_out_f32)),
-                 "b200_decode_linear: fused LayerNorm needs beta, a zeroed counter, an fp32 output with n <= 1024, n and ldo "
-                 "multiples of 4, and no position shift / split / argmax");
   const int G = decode_linear_groups(a->n);
   const int grid = (a->n + 8 * G - 1) / (8 * G);
   cudaError_t err;

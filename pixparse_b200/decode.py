@@ -5,7 +5,7 @@ The reference loop (/root/reference/src/pixparse/utils/ocr_utils.py:165-197) re-
 through the single-token kernels of ``csrc/decode.cu`` (weight-streaming linears for <= 16 rows, one-query attention
 over the caches, LM head fused with the argmax); the position and the generated ids live in device memory, so the whole
 step is a fixed kernel sequence that is captured once and replayed -- no host work, no logits in HBM, no host
-synchronisation until the caller wants the ids (or, with ``stop_on_eos``, one 12-byte read every ``check_every`` steps).
+synchronisation until the caller wants the ids (or, with ``stop_on_eos``, one 4-byte read every ``check_every`` steps).
 
 Same arithmetic contract as the teacher-forced path it replaces (bf16 operands, fp32 accumulation, bf16 q / k / v /
 attention / GELU outputs, fp32 residual stream, logits rounded to bf16 before the argmax); decoder self-attention hides
@@ -17,7 +17,7 @@ import torch
 
 from . import _lib, ops
 
-MAX_PAGES = 16      # activation rows per decode_linear launch (csrc/decode.cu DL_M); larger batches run in chunks
+MAX_PAGES = 16      # activation rows per decode_linear launch (csrc/decode.cu DL_M); larger batches take TextDecoderHf.forward(past_key_values=...)
 
 
 class GreedyDecodeSession:
@@ -58,12 +58,11 @@ class GreedyDecodeSession:
         self.eos_id = None
         self.pad_id = None
         self.pdl = os.environ.get("PIXPARSE_B200_DECODE_PDL", "1") != "0"
-        # PIXPARSE_B200_DECODE_FUSE bit 0: one launch for the packed q | k | v projection (default, -1.5 %); bit 1: LayerNorm
-        # run by the last CTA of the producing linear (measured 10 % SLOWER than its own 4-CTA launch under PDL: the
-        # grid-wide fence + ticket in every CTA and a one-CTA tail cost more than a kernel boundary; opt-in only)
-        fuse = int(os.environ.get("PIXPARSE_B200_DECODE_FUSE", "1"))      # bit 0: packed q | k | v, bit 1: LayerNorm
-        self.fuse_qkv, self.fuse_ln = bool(fuse & 1), bool(fuse & 2) and D <= 1024
-        self.ln_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        # one launch for the packed q | k | v projection (q dense, k | v appended to the cache): -1.5 % against two launches.
+        # (LayerNorm run by the last CTA of the producing linear was tried and measured 10 % SLOWER than its own 4-CTA
+        # launch under PDL -- a grid-wide fence + ticket in every CTA and a one-CTA tail cost more than a kernel boundary --
+        # and cost every linear 30 registers: removed, profiles/r02_decode_ab.txt)
+        self.fuse_qkv = os.environ.get("PIXPARSE_B200_DECODE_FUSE", "1") != "0"
 
     # ---- one decode step (enqueue only; every per-step quantity is read from device memory) -------------------------
     def _step(self):
@@ -88,16 +87,9 @@ class GreedyDecodeSession:
             h16, h32 = self.h16[cur], self.h32[cur]
             n16, n32 = self.h16[cur ^ 1], self.h32[cur ^ 1]
 
-            def post_ln(name, o16, o32):
-                """LayerNorm(self.u32) -> (o16, o32): fused behind the producing linear, or its own launch."""
-                if self.fuse_ln:
-                    return (ar.w32(k + name + ".w"), ar.w32(k + name + ".b"), eps, o16, o32, self.ln_counter)
-                return None
-
             def ln_after(name, o16, o32):
-                if not self.fuse_ln:
-                    ops.layernorm_fwd(self.u32, ar.w32(k + name + ".w"), ar.w32(k + name + ".b"), eps,
-                                      out=(o16, o32, self.mean, self.rstd))
+                ops.layernorm_fwd(self.u32, ar.w32(k + name + ".w"), ar.w32(k + name + ".b"), eps,
+                                  out=(o16, o32, self.mean, self.rstd))
             # self-attention: packed q | k | v projection; q dense, k | v appended to the cache at the device-side position
             wqkv = ar.span(k + "sa.q.w", k + "sa.v.w", "w16").view(3 * D, D)
             bqkv = ar.span(k + "sa.q.b", k + "sa.v.b", "w32")
@@ -111,20 +103,17 @@ class GreedyDecodeSession:
             ops.decode_attention(self.q16, self.self_kv[j], self.self_kv[j], self.a16, B=B, H=H, ld_kv=2 * D,
                                  kv_bstride=self.t_max * 2 * D, k_col0=0, v_col0=D, pos=self.pos, key_ids=self.ids,
                                  pad_id=self.pad_id)
-            ops.decode_linear(self.a16, ar.w16(k + "sa.o.w"), M=B, out32=self.u32, bias=ar.w32(k + "sa.o.b"), resid=h32,
-                              ln=post_ln("sa_ln", n16, n32))
+            ops.decode_linear(self.a16, ar.w16(k + "sa.o.w"), M=B, out32=self.u32, bias=ar.w32(k + "sa.o.b"), resid=h32)
             ln_after("sa_ln", n16, n32)
             # cross-attention over the cached projection of the image tokens
             ops.decode_linear(n16, ar.w16(k + "ca.q.w"), M=B, out16=self.q16, bias=ar.w32(k + "ca.q.b"))
             ops.decode_attention(self.q16, self.cross_kv[j], self.cross_kv[j], self.a16, B=B, H=H, ld_kv=2 * D,
                                  kv_bstride=S * 2 * D, k_col0=0, v_col0=D, sk=S)
-            ops.decode_linear(self.a16, ar.w16(k + "ca.o.w"), M=B, out32=self.u32, bias=ar.w32(k + "ca.o.b"), resid=n32,
-                              ln=post_ln("ca_ln", h16, h32))
+            ops.decode_linear(self.a16, ar.w16(k + "ca.o.w"), M=B, out32=self.u32, bias=ar.w32(k + "ca.o.b"), resid=n32)
             ln_after("ca_ln", h16, h32)
             # feed-forward
             ops.decode_linear(h16, ar.w16(k + "fc1.w"), M=B, out16=self.g16, bias=ar.w32(k + "fc1.b"), act=1)
-            ops.decode_linear(self.g16, ar.w16(k + "fc2.w"), M=B, out32=self.u32, bias=ar.w32(k + "fc2.b"), resid=h32,
-                              ln=post_ln("f_ln", n16, n32))
+            ops.decode_linear(self.g16, ar.w16(k + "fc2.w"), M=B, out32=self.u32, bias=ar.w32(k + "fc2.b"), resid=h32)
             ln_after("f_ln", n16, n32)
             cur ^= 1
         # LM head (tied embedding) fused with the argmax, then: append the token, EOS bookkeeping, pos += 1

@@ -256,12 +256,11 @@ def decode_linear_ctas(n):
 
 
 def decode_linear(x, w, *, M, out16=None, out32=None, bias=None, resid=None, act=0, pos=None, out_pos_stride=0,
-                  argmax_partial=None, ldo=None, split=None, ln=None):
+                  argmax_partial=None, ldo=None, split=None):
     """y[M, N] = x[M, K] w[N, K]^T (+ bias) (act=1: GELU) (+ resid fp32), M <= 16. Outputs bf16 (out16) and / or fp32 (out32)
     with row pitch ldo (default: their stride(0)), shifted by pos[0] * out_pos_stride elements when pos (device int32) is
     given. argmax_partial: nothing is stored, the per-CTA (max, argmax) keys of the bf16-rounded outputs are.
-    split = (n_split, out2, ldo2): columns >= n_split go to out2 (bf16) and only they take the position shift.
-    ln = (gamma, beta, eps, ln_out16, ln_out32, counter): LayerNorm of the out32 rows fused behind the linear."""
+    split = (n_split, out2, ldo2): columns >= n_split go to out2 (bf16) and only they take the position shift."""
     assert x.dtype == BF16 and w.dtype == BF16 and x.dim() == 2 and w.dim() == 2
     N, K = w.shape
     assert x.shape[1] == K and x.shape[0] >= M
@@ -269,13 +268,10 @@ def decode_linear(x, w, *, M, out16=None, out32=None, bias=None, resid=None, act
         ref = out16 if out16 is not None else out32
         ldo = ref.stride(0) if ref is not None else 0
     n_split, out2, ldo2 = split if split is not None else (0, None, 0)
-    g, b, eps, l16, l32, cnt = ln if ln is not None else (None, None, 0.0, None, None, None)
     args = _lib.DecodeLinearArgs(m=M, x=ptr(x), ldx=_ld(x), w=ptr(w), ldw=_ld(w), bias=ptr(bias), resid=ptr(resid),
                                  ld_resid=_ld(resid) if resid is not None else 0, out_bf16=ptr(out16), out_f32=ptr(out32),
                                  ldo=ldo, pos=ptr(pos), out_pos_stride=out_pos_stride, argmax_partial=ptr(argmax_partial),
-                                 n=N, k=K, act=act, n_split=int(n_split), out2_bf16=ptr(out2), ldo2=int(ldo2),
-                                 ln_gamma=ptr(g), ln_beta=ptr(b), ln_out_bf16=ptr(l16), ln_out_f32=ptr(l32),
-                                 ln_counter=ptr(cnt), ln_eps=float(eps))
+                                 n=N, k=K, act=act, n_split=int(n_split), out2_bf16=ptr(out2), ldo2=int(ldo2))
     call("b200_decode_linear", args, stream())
 
 

@@ -502,28 +502,14 @@ def test_decode_linear(cuda_lib, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(16, 1024, 1024), (3, 768, 3072)])
-def test_decode_linear_fused_layernorm_and_split_output(cuda_lib, M, N, K):
-    """(a) LayerNorm of the finished fp32 rows fused behind the linear (run by the CTA that finishes last; the ticket
-    counter must be back at zero so the next launch can reuse it); (b) the packed q | k | v form: columns below n_split
-    dense and unshifted, the rest appended to a [B, T_max, 2D] cache at the device-side position."""
+def test_decode_linear_split_output(cuda_lib, M, N, K):
+    """The packed q | k | v form: columns below n_split dense and unshifted, the rest appended to a [B, T_max, 2D] cache at
+    the device-side position."""
     from pixparse_b200 import ops
     torch.manual_seed(8)
     x = torch.randn((16, K), device=DEV).bfloat16()
     w = (torch.randn((N, K), device=DEV) * K ** -0.5).bfloat16()
-    bias, resid = torch.randn((N,), device=DEV), torch.randn((16, N), device=DEV) * 3
-    gamma, beta = torch.rand((N,), device=DEV) + 0.5, torch.randn((N,), device=DEV)
-    counter = torch.zeros(1, device=DEV, dtype=torch.int32)
-    ref = x[:M].float() @ w.float().t() + bias + resid[:M]
-    want = F.layer_norm(ref, (N,), gamma, beta, 1e-5)
-    for _ in range(2):      # twice: the counter is reusable
-        u32 = torch.zeros((16, N), device=DEV)
-        l16 = torch.zeros((16, N), device=DEV, dtype=torch.bfloat16)
-        l32 = torch.zeros((16, N), device=DEV)
-        ops.decode_linear(x, w, M=M, out32=u32, bias=bias, resid=resid, ln=(gamma, beta, 1e-5, l16, l32, counter))
-        assert rel_err(u32[:M], ref) < 1e-5
-        assert rel_err(l32[:M], want) < 1e-5 and rel_err(l16[:M], want) < 4e-3
-        assert (l32[M:] == 0).all() and int(counter.item()) == 0
-    # split output
+    bias = torch.randn((N,), device=DEV)
     D = N // 4
     t_max = 7
     q = torch.zeros((16, D), device=DEV, dtype=torch.bfloat16)
