@@ -88,6 +88,31 @@ def build(verbose=False, force=False):
     return LIB_PATH
 
 
+def build_variant(name, extra_flags, only=None):
+    """A/B builds: csrc/libab_<name>.so compiled with extra nvcc flags (e.g. -DB200_GEMM_NAUX=1); loaded through
+    PIXPARSE_B200_LIB (scripts/gpu_ab.sh, scripts/gpu_gemm_ab.sh). Objects of files not in `only` are reused."""
+    out_dir = os.path.join(CSRC, "build", "ab_" + name)
+    os.makedirs(out_dir, exist_ok=True)
+    build()
+    objs = []
+    for src in _sources():
+        if only is not None and src not in only:
+            objs.append(os.path.join(OBJ_DIR, src[:-3] + ".o"))
+            continue
+        obj = os.path.join(out_dir, src[:-3] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        objs.append(obj)
+    lib = os.path.join(CSRC, f"libab_{name}.so")
+    res = subprocess.run([_nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
     path = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
     print(path)

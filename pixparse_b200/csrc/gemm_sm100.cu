@@ -57,7 +57,10 @@ static int g_force_single_cta = 0;      // bring-up / A-B switch: 1 = never use 
 // stages its own 128 rows of A and BN / 2 rows of B, so a k-block costs 32 KB of L2 -> SM traffic per SM instead of 48.
 // Epilogues with an aux operand (DGELU: saved pre-activation, RESID: residual stream) stage it in a second 16 KB tile per
 // epilogue group, which costs the ring one stage.
-template <int BN, int CG, int EPI>
+// DEEP (RESID with a long reduction only): one aux tile per epilogue group instead of two, which buys the operand ring a fifth
+// stage. Measured at the encoder shapes (profiles/r02_experiments_no_gain.txt): fc2 + residual (K = 3072, the A operand
+// streams 198 MB from HBM) 0.138 -> 0.130 ms, but proj + residual (K = 768, epilogue-bound) 0.057 -> 0.061 ms.
+template <int BN, int CG, int EPI, bool DEEP = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
@@ -65,7 +68,7 @@ struct GemmCfg {
   static constexpr bool HAS_AUX = (EPI == B200_EPI_DGELU_BF16 || EPI == B200_EPI_RESID_F32);
   // aux tiles per epilogue group: two (prefetch distance of two rounds: one round is shorter than an HBM round trip
   // under load) wherever the ring can spare the space
-  static constexpr int NAUX = HAS_AUX ? ((CG == 2 || BN == 128) ? 2 : 1) : 0;
+  static constexpr int NAUX = HAS_AUX ? (((CG == 2 || BN == 128) && !DEEP) ? 2 : 1) : 0;
   static constexpr int EPI_GROUP_BYTES = (1 + (EPI == B200_EPI_GELU_BF16 ? 1 : NAUX)) * EPI_BUF_BYTES;
   static constexpr int TAIL_BYTES = 256 /* barriers */ + 1024 /* bias */ + 1024 /* alignment slack */;
   static constexpr int MAX_STAGES = (232448 - TAIL_BYTES - 2 * EPI_GROUP_BYTES) / STAGE_BYTES;
@@ -239,12 +242,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG, EPI>;
+  using Cfg = GemmCfg<BN, CG, EPI, DEEP>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -773,11 +776,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = false>
 static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                           const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG, DROP>;
-  constexpr int SMEM = GemmCfg<BN, CG, EPI>::SMEM_BYTES;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG, DROP, DEEP>;
+  constexpr int SMEM = GemmCfg<BN, CG, EPI, DEEP>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -795,10 +798,18 @@ template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                        const GemmParams& p, int grid, bool cta_pairs, cudaStream_t stream) {
   constexpr bool CAN_DROP = EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16;
+  // fc2 + residual of the forward pass (K-major operands, K >= 2048): the deeper operand ring (GemmCfg DEEP)
+  constexpr bool HAS_DEEP = EPI == B200_EPI_RESID_F32 && !A_MN && !B_MN;
+  const bool deep = HAS_DEEP && p.K >= 2048;
   if (CAN_DROP && p.drop_threshold16 != 0u) {
-    if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP>(ta, tb, to, to2, p, grid, stream);
+    if (BN == 256 && cta_pairs) {
+      if (deep) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP, HAS_DEEP>(ta, tb, to, to2, p, grid, stream);
+      return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP>(ta, tb, to, to2, p, grid, stream);
+    }
     return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, CAN_DROP>(ta, tb, to, to2, p, grid, stream);
   }
+  if (BN == 256 && cta_pairs && deep)
+    return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false, HAS_DEEP>(ta, tb, to, to2, p, grid, stream);
   if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false>(ta, tb, to, to2, p, grid, stream);
   return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, false>(ta, tb, to, to2, p, grid, stream);
 }

@@ -20,6 +20,14 @@ elif which == "resid":
     A = torch.randn((M, D), device="cuda").bfloat16(); B = torch.randn((D, D), device="cuda").bfloat16() * 0.05
     x = torch.randn((M, D), device="cuda"); o = torch.empty_like(x); bias = torch.randn(D, device="cuda")
     fn = lambda: ops.gemm(A, B, epi=ops.EPI_RESID_F32, bias=bias, aux=x, out=o)
+elif which == "resid3072":      # fc2 forward: K = 3072, fp32 residual in / out
+    A = torch.randn((M, F), device="cuda").bfloat16(); B = torch.randn((D, F), device="cuda").bfloat16() * 0.05
+    x = torch.randn((M, D), device="cuda"); o = torch.empty_like(x); bias = torch.randn(D, device="cuda")
+    fn = lambda: ops.gemm(A, B, epi=ops.EPI_RESID_F32, bias=bias, aux=x, out=o)
+elif which == "dgrad3072":      # fc1 dgrad: same M, N, K as resid3072 with a plain bf16 store
+    A = torch.randn((M, F), device="cuda").bfloat16(); B = torch.randn((F, D), device="cuda").bfloat16() * 0.05
+    o = torch.empty((M, D), device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.gemm(A, B, b_mn=True, out=o)
 elif which == "store3072":      # the GELU GEMM's shape with a plain bf16 store: isolates the cost of the activation epilogue
     A = torch.randn((M, D), device="cuda").bfloat16(); B = torch.randn((F, D), device="cuda").bfloat16() * 0.05
     bias = torch.randn(F, device="cuda"); o = torch.empty((M, F), device="cuda", dtype=torch.bfloat16)

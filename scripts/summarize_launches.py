@@ -19,10 +19,10 @@ for row in r:
 def short(n):
     n = re.sub(r"\(.*", "", n)
     n = n.replace("b200::", "")
-    m = re.match(r"gemm_kernel<(\d+), *(true|false|\(bool\)[01]), *(true|false|\(bool\)[01]), *(\d+)>", n)
+    m = re.match(r"gemm_kernel<(\d+), *(true|false|\(bool\)[01]|[01]), *(true|false|\(bool\)[01]|[01]), *(\d+)", n)
     if m:
         epi = {0:"store_bf16",1:"gelu",2:"resid_f32",3:"dgelu",4:"reduce_f32(wgrad)",5:"store_f32"}[int(m.group(4))]
-        a = "MN" if m.group(2) in ("true","(bool)1") else "K"; b = "MN" if m.group(3) in ("true","(bool)1") else "K"
+        a = "MN" if m.group(2) in ("true","(bool)1","1") else "K"; b = "MN" if m.group(3) in ("true","(bool)1","1") else "K"
         return f"gemm<BN{m.group(1)},{a}x{b},{epi}>"
     return n[:70]
 agg = collections.OrderedDict()

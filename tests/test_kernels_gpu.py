@@ -37,7 +37,9 @@ def test_gemm_layouts(cuda_lib, a_mn, b_mn, M, N, K, bn):
 # (1009, 776, 320): ragged M / N / K inside single tiles; (129, 512, 64) and (300, 256, 128): CTA pairs whose second CTA is
 # (almost) empty; (9000, 1536, 192): 216 pair tiles on 74 pairs -> every CTA loops over several tiles (accumulator-stage
 # phases, aux prefetch and bias restaging across tiles); (100, 768, 256): single-CTA 256-wide tiles (M <= 128)
-@pytest.mark.parametrize("M,N,K", [(1009, 776, 320), (129, 512, 64), (300, 256, 128), (9000, 1536, 192), (100, 768, 256)])
+# (600, 520, 2112): K >= 2048 selects the residual epilogue's deep-ring variant (one aux tile per group, five operand stages)
+@pytest.mark.parametrize("M,N,K", [(1009, 776, 320), (129, 512, 64), (300, 256, 128), (9000, 1536, 192), (100, 768, 256),
+                                   (600, 520, 2112)])
 @pytest.mark.parametrize("single_cta", [0, 1])
 def test_gemm_epilogues(cuda_lib, M, N, K, single_cta):
     from pixparse_b200 import ops, _lib
