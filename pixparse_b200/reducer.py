@@ -117,9 +117,18 @@ class GradReducer:
 # ----------------------------------------------------------------------------------------------------------------------
 class _SymmetricTransport:
     """Peer-addressable buffers through torch symmetric memory (CUDA VMM handles exchanged at rendezvous): a ``copy_``
-    into a peer's buffer is a device-to-device memcpy that the COPY ENGINES carry over NVLink -- no SM is involved."""
+    into a peer's buffer is a device-to-device memcpy that the COPY ENGINES carry over NVLink -- no SM is involved.
+
+    The barrier is SM-free as well: stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32, executed by the
+    GPU's front end) on a row of flags in symmetric memory -- every rank writes the barrier's sequence number into its
+    slot of every peer's row, then waits for all slots of its own row to reach it. A write-value is ordered after the
+    copies that precede it on the stream, so a rank that sees a peer's number also sees that peer's pushes. (A collective
+    kernel for the barrier cannot share an SM with the step's persistent GEMM CTAs, which own the whole register file:
+    each of the ~25 barriers of a step then holds back one GEMM CTA, i.e. the whole statically scheduled GEMM, for its
+    duration. PIXPARSE_B200_P2P_BARRIER=nccl keeps the 1-element NCCL all-reduce.)"""
 
     def __init__(self, numel_by_name, device, group):
+        import os
         import torch.distributed._symmetric_memory as symm
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.group = group if group is not None else dist.group.WORLD
@@ -131,13 +140,60 @@ class _SymmetricTransport:
             self.local[name] = t
             self.peer[name] = [t if r == self.rank else hdl.get_buffer(r, (numel,), torch.float32) for r in range(self.world)]
         self._flag = torch.zeros(1, device=device)
+        self._drv = None
+        if os.environ.get("PIXPARSE_B200_P2P_BARRIER", "memop") == "memop":
+            try:
+                from cuda.bindings import driver as drv
+            except ImportError:
+                try:
+                    from cuda import cuda as drv
+                except ImportError:
+                    drv = None
+            if drv is not None:
+                flags = symm.empty(64, dtype=torch.int32, device=device)      # slot s: written by rank s
+                flags.zero_()
+                fh = symm.rendezvous(flags, self.group)
+                self._flags = flags
+                self._flag_ptrs = [int(p) for p in fh.buffer_ptrs]
+                self._seq = 0
+                self._drv = drv
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)      # every rank's flags are zeroed before anyone writes one
+        if self._drv is not None:
+            # one round trip now: a driver / device without stream memory operations on peer memory must show up here, on
+            # every rank alike, not in the middle of a step
+            ok = torch.ones(1, device=device)
+            try:
+                self.barrier()
+                torch.cuda.synchronize(device)
+            except RuntimeError:
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if ok.item() == 0:
+                self._drv = None
 
     def push(self, peer, name, offset, src):
         self.peer[name][peer][offset:offset + src.numel()].copy_(src, non_blocking=True)
 
     def barrier(self):
-        # every rank's earlier pushes (same stream, in order) have landed once this tiny all-reduce completes anywhere
-        dist.all_reduce(self._flag, group=self.group)
+        """Stream-ordered: every rank's earlier pushes (same stream, in order) have landed once the stream gets past this."""
+        if self._drv is None:
+            dist.all_reduce(self._flag, group=self.group)      # tiny NCCL all-reduce on the current stream
+            return
+        drv = self._drv
+        self._seq = (self._seq + 1) & 0x7FFFFFFF
+        stream = torch.cuda.current_stream().cuda_stream
+        me = self.rank
+        for d in range(1, self.world):
+            p = (me + d) % self.world
+            (err,) = drv.cuStreamWriteValue32(stream, self._flag_ptrs[p] + 4 * me, self._seq, 0)
+            if int(err) != 0:
+                raise RuntimeError(f"cuStreamWriteValue32 failed: {err}")
+        for d in range(1, self.world):
+            p = (me + d) % self.world
+            (err,) = drv.cuStreamWaitValue32(stream, self._flag_ptrs[me] + 4 * p, self._seq, 0)      # cyclic >=
+            if int(err) != 0:
+                raise RuntimeError(f"cuStreamWaitValue32 failed: {err}")
 
 
 class _ExchangeTransport:
@@ -196,6 +252,12 @@ class P2PGradReducer(GradReducer):
         self.flat = arena.g32
         self.stage = self.tr.local["stage"]
         self._cursor = 0
+        import os
+        self._dry = os.environ.get("PIXPARSE_B200_P2P_DRY", "0") == "1"
+        if self.cuda:
+            # the per-bucket sum kernel should take the first SMs a finishing GEMM frees (its partly empty last wave)
+            # instead of queueing behind the next persistent kernel
+            self.comm_stream = torch.cuda.Stream(device=arena.g32.device, priority=-1)
 
     def begin(self):
         super().begin()
@@ -209,6 +271,8 @@ class P2PGradReducer(GradReducer):
 
     def _exchange(self, lo, hi):
         from . import ops
+        if self._dry:      # diagnostics: the symmetric-memory arena without any exchange
+            return
         w, me = self.world_size, self.rank
         c, shares = self.shares(lo, hi)
         base = self._cursor
@@ -242,7 +306,7 @@ class P2PGradReducer(GradReducer):
         if not self.enabled:
             return
         super().finish()
-        if self.world_size > 1:
+        if self.world_size > 1 and not self._dry:
             # all step-4 pushes into this rank's arena have landed before the optimizer reads it
             if self.cuda:
                 with torch.cuda.stream(self.comm_stream):
