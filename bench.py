@@ -349,6 +349,8 @@ def time_train_config(cfgname, env, steps, warmup, batch=None, dropout_off=False
     sampler = ClockSampler(dev.index if dev.index is not None else 0)
     sampler.start()
     _lib.reset_launch_count()
+    if task.reducer is not None:
+        task.reducer.measure_exposed = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     last = None
@@ -356,7 +358,10 @@ def time_train_config(cfgname, env, steps, warmup, batch=None, dropout_off=False
         last = device_step(i)
     e1.record()
     barrier()
+    if task.reducer is not None:
+        task.reducer.measure_exposed = False
     launches = _lib.launch_count()
+    exposed = task.reducer.exposed_ms() if (task.reducer is not None and hasattr(task.reducer, "exposed_ms")) else None
     own_ms = e0.elapsed_time(e1) / steps
     ms_step = max_over_ranks(e0.elapsed_time(e1)) / steps
     per_rank = [own_ms]
@@ -380,7 +385,7 @@ def time_train_config(cfgname, env, steps, warmup, batch=None, dropout_off=False
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / steps
     sampler.stop()
     res = {"task": task, "device_step": device_step, "barrier": barrier, "B": B, "ms_step": ms_step, "ms_e2e": ms_e2e,
-           "loss": loss_val, "launches": launches, "per_rank_ms": per_rank, "h2d_bytes": h2d_bytes, "clocks": sampler.summary(),
+           "loss": loss_val, "launches": launches, "per_rank_ms": per_rank, "exchange_exposed_ms": exposed, "h2d_bytes": h2d_bytes, "clocks": sampler.summary(),
            "pages_per_s": world * B / (ms_step * 1e-3), "e2e_pages_per_s": world * B / (ms_e2e * 1e-3)}
     return res
 
@@ -716,6 +721,7 @@ def run_b200_arm(args):
         "loss": res["loss"],
         "clocks": res["clocks"],
         "per_rank_ms": res["per_rank_ms"],
+        "exchange_exposed_ms": res["exchange_exposed_ms"],      # compute stream waiting for the gradient exchange after backward
         "e2e": {"value": res["e2e_pages_per_s"], "unit": "pages/s", "ms_per_step": res["ms_e2e"],
                 "h2d_bytes_per_step": res["h2d_bytes"], "d2h_bytes_per_step": 4},
         "gpu_launches": res["launches"],

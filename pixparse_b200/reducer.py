@@ -26,6 +26,8 @@ class GradReducer:
         self.backend = dist.get_backend(process_group) if dist.is_initialized() else None
         self._pending = None       # [lo, hi) finished by backward but not yet issued
         self._done = []            # issued ranges (for bookkeeping / tests)
+        self.measure_exposed = False
+        self._exposed = []
         self.enabled = True        # False inside no_sync() (gradient accumulation micro-steps)
 
     # -- context manager mirroring DDP.no_sync()
@@ -90,10 +92,30 @@ class GradReducer:
             self._issue(*self._pending)
             self._pending = None
 
+    def exposed_ms(self):
+        """Mean device time the compute stream spent waiting for the exchange at the end of backward (events recorded by
+        finish() when `measure_exposed` is set; call after a synchronize)."""
+        if not self._exposed:
+            return None
+        ms = [a.elapsed_time(b) for a, b in self._exposed]
+        self._exposed = []
+        return sum(ms) / len(ms)
+
     def finish(self):
         """Issue whatever is left (everything not yet covered) and make the compute stream wait for NCCL."""
         if not self.enabled:
             return
+        if self.measure_exposed and self.cuda:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.flat.device))
+            self._finish()
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.flat.device))
+            self._exposed.append((e0, e1))
+            return
+        self._finish()
+
+    def _finish(self):
         if self._pending is not None:
             self._issue(*self._pending)
             self._pending = None
@@ -302,10 +324,8 @@ class P2PGradReducer(GradReducer):
         lo = view.storage_offset() - self.flat.storage_offset()
         self._exchange(lo, lo + view.numel())
 
-    def finish(self):
-        if not self.enabled:
-            return
-        super().finish()
+    def _finish(self):
+        super()._finish()
         if self.world_size > 1 and not self._dry:
             # all step-4 pushes into this rank's arena have landed before the optimizer reads it
             if self.cuda:
