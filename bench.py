@@ -672,7 +672,7 @@ def run_b200_arm(args):
     # DRAM traffic per launch from the committed ncu --set full captures (profiles/), weighted by this step's call mix
     traffic, traffic_detail = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm_dram_traffic.json")) as fh:
             cap = json.load(fh)["variants"]
         tot_b, tot_c = 0.0, 0
         traffic_detail = {}
@@ -686,7 +686,7 @@ def run_b200_arm(args):
         if tot_c:
             traffic = tot_b / tot_c
             traffic_detail["note"] = ("mean DRAM bytes per launch over the captured variants (each at its encoder shape), "
-                                      "weighted by calls per step; source profiles/r01_gemm_dram_traffic.json")
+                                      "weighted by calls per step; source profiles/r02_gemm_dram_traffic.json")
     except (OSError, KeyError, ValueError):
         pass
     # attention: algorithmic FLOPs of the step's attention calls (full S x S / T x T / T x S, bwd = 2.5 x fwd)
