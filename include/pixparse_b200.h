@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 
 /* ---- runtime ---------------------------------------------------------------------------------- */
 const char* b200_last_error(void);
@@ -82,6 +82,13 @@ typedef struct B200GemmArgs {
   int block_n;           /* 0 = choose; 128 or 256 */
   float drop_p;
   unsigned int drop_seed;
+  /* Dynamic tile scheduling. NULL: the persistent grid deals its work items statically (CTA i takes items i, i + grid, ...).
+   * Otherwise a caller-owned device counter that is ZERO when the kernel starts; CTAs draw items from it with one
+   * atomicAdd each and the kernel leaves it at zero again, so one counter serves any number of launches that do not
+   * overlap in time (kernels that may run concurrently, e.g. on two streams, need different counters). Results are
+   * identical; what changes is that kernels sharing the GPU across streams split its SMs work-conservingly (a weight
+   * gradient on a side stream fills the partly empty last wave of the main stream's kernel). */
+  unsigned int* tile_counter;
 } B200GemmArgs;
 int b200_gemm_bf16(const B200GemmArgs* args, void* stream);
 

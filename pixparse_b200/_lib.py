@@ -18,7 +18,7 @@ EPI_RESID_F32 = 2
 EPI_DGELU_BF16 = 3
 EPI_REDUCE_F32 = 4
 EPI_STORE_F32 = 5
-ABI_VERSION = 2      # B200_ABI_VERSION of include/pixparse_b200.h
+ABI_VERSION = 3      # B200_ABI_VERSION of include/pixparse_b200.h
 
 
 class B200Error(RuntimeError):
@@ -68,7 +68,7 @@ class GemmArgs(_Args):
     _fields_ = [("struct_size", _U), ("epilogue", _I), ("a", _P), ("lda", _L), ("a_mn_major", _I), ("b", _P), ("ldb", _L),
                 ("b_mn_major", _I), ("m", _I), ("n", _I), ("k", _I), ("out", _P), ("ldo", _L), ("out2", _P), ("ldo2", _L),
                 ("bias", _P), ("aux", _P), ("ld_aux", _L), ("bias_grad", _P), ("splits", _I), ("block_n", _I),
-                ("drop_p", _F), ("drop_seed", _U)]
+                ("drop_p", _F), ("drop_seed", _U), ("tile_counter", _P)]
 
 
 class AttentionFwdArgs(_Args):

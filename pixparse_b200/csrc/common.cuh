@@ -428,6 +428,19 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+// polled shared-memory words (the tile ring of the GEMM's dynamic scheduler): volatile so that a spin loop re-reads them;
+// the second form stores into the same offset of another CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts32_cluster(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.volatile.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");

@@ -47,6 +47,9 @@ struct GemmParams {
   // REDUCE_F32 + A MN-major (weight gradients): bias_grad[m] += sum_k A(m, k), summed from the staged A tiles by the two
   // otherwise idle control warps (10, 11); the k-blocks are dealt round-robin to the n_tiles items that share an A panel
   float* bias_grad;
+  // dynamic tile scheduler: work items are handed out through this device counter (zero on entry, left at zero) instead
+  // of the static round-robin deal; nullptr = static. See TileSched.
+  unsigned int* tile_counter;
 };
 
 // debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
@@ -70,11 +73,64 @@ struct GemmCfg {
   // under load) wherever the ring can spare the space
   static constexpr int NAUX = HAS_AUX ? (((CG == 2 || BN == 128) && !DEEP) ? 2 : 1) : 0;
   static constexpr int EPI_GROUP_BYTES = (1 + (EPI == B200_EPI_GELU_BF16 ? 1 : NAUX)) * EPI_BUF_BYTES;
-  static constexpr int TAIL_BYTES = 256 /* barriers */ + 1024 /* bias */ + 1024 /* alignment slack */;
+  static constexpr int TAIL_BYTES = 256 /* barriers */ + 1024 /* bias */ + 64 /* tile ring */ + 1024 /* alignment slack */;
   static constexpr int MAX_STAGES = (232448 - TAIL_BYTES - 2 * EPI_GROUP_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES < 6 ? MAX_STAGES : 6;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (256 or 512 columns: powers of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_GROUP_BYTES + TAIL_BYTES;
+};
+
+// ---- work distribution over the persistent grid -------------------------------------------------------------------
+// Static (tile_counter == nullptr): worker i (a CTA, or a CTA pair) takes items i, i + n_workers, ... Every warp role
+// computes that sequence on its own.
+// Dynamic: items come from a device-wide counter, one atomicAdd per item by the leader CTA's producer warp, and are
+// published to all warp roles of the worker through a small ring of tagged words in shared memory (the leader writes
+// its peer's ring through the cluster window). Why: every kernel of the step owns whole SMs (registers and shared
+// memory), so a second stream's kernel -- the weight gradients, which nothing waits for before the optimizer -- can only
+// use the SMs a kernel frees in its partly empty last wave, and with a static deal a CTA that starts late still holds a
+// full share: the kernel merely ends later. With the counter a late CTA finds less (or nothing) left, early ones take
+// more, and concurrent kernels share the machine work-conservingly.
+//   word = tag << 20 | item, tag = (seq + 1) & 0xfff for the worker's seq-th item (a zeroed ring matches no seq);
+//   item == total marks the end. The ring (16 entries) outlives every reader: the producer runs at most STAGES
+//   k-blocks (<= 6 items) ahead of the MMA warp, which runs at most two accumulator stages ahead of the epilogue.
+//   The counter cleans up after itself: a launch performs exactly total + n_workers fetches (every worker ends on
+//   its first empty-handed one), so whoever draws ticket total + n_workers - 1 resets it to zero.
+constexpr int SCHED_RING = 16;
+constexpr int SCHED_MAX_ITEMS = (1 << 20) - 1;
+
+struct TileSched {
+  uint32_t ring_s;          // shared address of this CTA's ring
+  int worker, n_workers, total;
+  unsigned int* counter;    // nullptr = static
+
+  __device__ __forceinline__ bool dynamic() const { return counter != nullptr; }
+  // the worker's seq-th work item (>= total: none left); dynamic: spins until the producer has published it
+  __device__ __forceinline__ int get(int seq) const {
+    if (!dynamic()) {
+      const long long w = (long long)worker + (long long)seq * n_workers;
+      return w < total ? (int)w : total;
+    }
+    const uint32_t addr = ring_s + (uint32_t)(seq & (SCHED_RING - 1)) * 4u;
+    const uint32_t tag = (uint32_t)(seq + 1) & 0xfffu;
+    uint32_t v;
+    do {
+      v = lds32_volatile(addr);
+    } while ((v >> 20) != tag);
+    return (int)(v & 0xfffffu);
+  }
+  // leader CTA, producer warp (all lanes call): draw the next item and publish it as the worker's seq-th
+  __device__ __forceinline__ void fetch_publish(int seq, bool pair) const {
+    if (elect_one()) {
+      const unsigned int t = atomicAdd(counter, 1u);
+      if (t == (unsigned int)(total + n_workers - 1)) atomicExch(counter, 0u);      // the last fetch of this launch
+      const uint32_t item = t < (unsigned int)total ? t : (uint32_t)total;
+      const uint32_t word = (((uint32_t)(seq + 1) & 0xfffu) << 20) | item;
+      const uint32_t addr = ring_s + (uint32_t)(seq & (SCHED_RING - 1)) * 4u;
+      sts32_volatile(addr, word);
+      if (pair) sts32_cluster(mapa_u32(addr, 1), word);
+    }
+    __syncwarp();
+  }
 };
 
 __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& n_tile, int& split) {
@@ -266,6 +322,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   constexpr bool CAN_BIASG = (EPI == B200_EPI_REDUCE_F32) && A_MN;
   const bool biasg = CAN_BIASG && p.bias_grad != nullptr;
   float* epi_bias = reinterpret_cast<float*>(epi_buf + 2 * Cfg::EPI_GROUP_BYTES + 256);   // 2 groups x 128 floats
+  uint32_t* sched_ring = reinterpret_cast<uint32_t*>(epi_buf + 2 * Cfg::EPI_GROUP_BYTES + 256 + 1024);   // [SCHED_RING]
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -295,6 +352,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_init(&aux_free_bar[2 * i + j], 128);
       }
     }
+    for (int i = 0; i < SCHED_RING; ++i) sched_ring[i] = 0u;
     fence_mbar_init();
   }
   if (warp == 10) {
@@ -314,6 +372,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   pdl_wait();      // prologue done; operands / outputs of the predecessor kernel are touched only from here on
 
   const int total_work = p.m_tiles * p.n_tiles * p.splits;
+  const TileSched sched{smem_u32(sched_ring), worker, n_workers, total_work, p.tile_counter};
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -323,7 +382,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = worker; w < total_work; w += n_workers) {
+      const bool fetcher = sched.dynamic() && cta_rank == 0;     // this warp draws the worker's items from the counter
+      if (fetcher) sched.fetch_publish(0, CG == 2);
+      for (int seq = 0;; ++seq) {
+        const int w = sched.get(seq);
+        if (w >= total_work) break;
         int m_tile, n_tile, split;
         decode_work(p, w, m_tile, n_tile, split);
         if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;      // this CTA's 128 rows of the pair's 256
@@ -379,6 +442,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             phase ^= 1;
           }
         }
+        // all loads of this item are issued: draw the next one (its latency hides behind the STAGES k-blocks in flight)
+        if (fetcher) sched.fetch_publish(seq + 1, CG == 2);
       }
     }
   } else if (warp == 9) {
@@ -389,7 +454,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = worker; w < total_work; w += n_workers) {
+      for (int seq = 0;; ++seq) {
+        const int w = sched.get(seq);
+        if (w >= total_work) break;
         int m_tile, n_tile, split;
         decode_work(p, w, m_tile, n_tile, split);
         const int kb0 = split * p.kb_per_split;
@@ -447,7 +514,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int chunk = warp - 10;
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = worker; w < total_work; w += n_workers) {
+    for (int seq = 0;; ++seq) {
+      const int w = sched.get(seq);
+      if (w >= total_work) break;
       int m_tile, n_tile, split;
       decode_work(p, w, m_tile, n_tile, split);
       if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
@@ -539,13 +608,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const float drop_sc = dropout_scale(p.drop_threshold16);
       constexpr int NAUX = AUX ? Cfg::NAUX : 1;              // aux tiles in flight = prefetch distance in rounds
       uint32_t aux_seq = 0;                                  // rounds consumed by this group: slot = seq % NAUX
-      // thread 0 of the group: start the aux load of the round `ahead` rounds after (work item w, round rd)
-      auto issue_aux = [&](int w, int rd, int ahead, uint32_t seq) {
+      // thread 0 of the group: start the aux load of the round `ahead` rounds after (the worker's wseq-th item, round rd).
+      // (dynamic scheduling: a later item is published once the loads of the item in front of it are issued, which
+      // does not depend on this warp -- the wait cannot deadlock)
+      auto issue_aux = [&](int wseq, int rd, int ahead, uint32_t seq) {
         rd += ahead;
         while (rd >= ROUNDS) {
           rd -= ROUNDS;
-          w += n_workers;
+          ++wseq;
         }
+        const int w = sched.get(wseq);
         if (w >= total_work) return;
         int m_t, n_t, sp;
         decode_work(p, w, m_t, n_t, sp);
@@ -556,9 +628,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     n_t * BN + (grp + 2 * rd) * CW, m_t * BM);
       };
       if (AUX && et == 0) {
-        for (int a = 0; a < NAUX; ++a) issue_aux(worker, 0, a, (uint32_t)a);
+        for (int a = 0; a < NAUX; ++a) issue_aux(0, 0, a, (uint32_t)a);
       }
-      for (int w = worker; w < total_work; w += n_workers) {
+      for (int wseq = 0;; ++wseq) {
+        const int w = sched.get(wseq);
+        if (w >= total_work) break;
         int m_tile, n_tile, split;
         decode_work(p, w, m_tile, n_tile, split);
         if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
@@ -597,7 +671,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 if (et == 0) {
                   // refill this aux tile for the round NAUX rounds ahead (possibly of a later tile) once all have read it
                   mbar_wait(&aux_free_bar[2 * grp + aslot], aphase);
-                  issue_aux(w, rd, NAUX, aux_seq);
+                  issue_aux(wseq, rd, NAUX, aux_seq);
                 }
                 ++aux_seq;
               }
@@ -702,7 +776,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (et == 0) tma_wait_group<0>();    // all bulk stores complete before the CTA exits
     } else
-    for (int w = worker; w < total_work; w += n_workers) {
+    for (int wseq = 0;; ++wseq) {
+      const int w = sched.get(wseq);
+      if (w >= total_work) break;
       int m_tile, n_tile, split;
       decode_work(p, w, m_tile, n_tile, split);
       if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
@@ -916,6 +992,8 @@ extern "C" int b200_gemm_bf16(const B200GemmArgs* args, void* stream_) {
   p.out = out; p.ldo = ldo; p.out2 = out2; p.ldo2 = ldo2;
   p.bias = bias; p.aux = aux; p.ld_aux = ld_aux;
   p.bias_grad = bias_grad;
+  // dynamic tile scheduler (caller-owned, zero-initialised counter); items must fit the 20-bit field of a ring word
+  p.tile_counter = ((long long)tiles * p.splits <= SCHED_MAX_ITEMS) ? args->tile_counter : nullptr;
   if (bias_grad != nullptr)
     B200_CHECK_ARG(epilogue == B200_EPI_REDUCE_F32 && a_mn_major,
                    "b200_gemm_bf16: bias_grad is fused only into weight gradients (REDUCE_F32 epilogue, A MN-major)");

@@ -114,6 +114,50 @@ class _Saved:
     pass
 
 
+class _SideLane:
+    """Work with no consumer before the optimizer (weight / bias gradients) on a second stream. Every kernel of the
+    step owns whole SMs, so the two streams do not run side by side on an SM; what the side stream gets are the SMs
+    the main stream's kernel frees in its partly empty last wave and the gaps between dependent kernels. That only
+    pays with the GEMM's dynamic tile scheduler (ops.gemm, B200GemmArgs.tile_counter): with a static deal a CTA that
+    starts late still holds a full share of its kernel. ``side`` = None runs everything inline on the current stream."""
+
+    def __init__(self, side, device):
+        self.side = side
+        self.main = torch.cuda.current_stream(device) if side is not None else None
+
+    def mark(self):
+        """Event at the current point of the main stream (None when inline)."""
+        if self.side is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        return ev
+
+    def run(self, fn, keep, after=None):
+        """Enqueue fn() on the side stream behind the main-stream point `after` (default: everything issued so far);
+        returns an event recorded after it. `keep`: tensors the side stream reads (they must outlive its kernels)."""
+        if self.side is None:
+            fn()
+            return None
+        self.side.wait_event(after if after is not None else self.mark())
+        with torch.cuda.stream(self.side):
+            fn()
+        done = torch.cuda.Event()
+        done.record(self.side)
+        for t in keep:
+            t.record_stream(self.side)
+        return done
+
+    def wait(self, ev):
+        """The main stream waits for a side-stream event (before it overwrites something that work reads)."""
+        if ev is not None:
+            self.main.wait_event(ev)
+
+    def join(self):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+
+
 class DecodeCache:
     """KV cache of one greedy-decoding session: per decoder layer the self-attention keys | values of
     every generated position ([B, T_max, 2D], appended in place) and the cross-attention K | V projection of the image
@@ -325,39 +369,9 @@ class CrullerEngine:
         dx32, dx16 = ops.layernorm_bwd(x, meanf, rstdf, ar.w32("vit.norm.w"), ar.grad("vit.norm.w"),
                                        ar.grad("vit.norm.b"), dy32=d_enc32)
         # Bias gradients ride on the weight-gradient GEMMs (their A operand is dY: B200GemmArgs.bias_grad), no colsum pass.
-        # Weight / bias gradients have no consumer before the optimizer, so they can run on a side stream and fill the
-        # partially empty last waves of the main stream's persistent kernels (opt-in: PIXPARSE_B200_SIDE_WGRAD=1).
-        side = self._side_stream() if self.side_wgrad and dx16.is_cuda else None
-        main = torch.cuda.current_stream(dx16.device) if side is not None else None
-
-        def mark():
-            """Event at the current point of the main stream (None without a side stream)."""
-            if side is None:
-                return None
-            ev = torch.cuda.Event()
-            ev.record(main)
-            return ev
-
-        def on_side(fn, keep, after=None):
-            """Enqueue fn() on the side stream behind the main-stream point `after` (default: everything issued so far);
-            returns an event recorded after it. `keep`: tensors the side stream reads (must outlive its kernels)."""
-            if side is None:
-                fn()
-                return None
-            ev = after if after is not None else mark()
-            side.wait_event(ev)
-            with torch.cuda.stream(side):
-                fn()
-            done = torch.cuda.Event()
-            done.record(side)
-            for t in keep:
-                t.record_stream(side)
-            return done
-
-        def wait(ev):
-            if ev is not None:
-                main.wait_event(ev)
-
+        # Weight / bias gradients have no consumer before the optimizer: they go to a side stream (_SideLane) right behind
+        # the kernel that produces their dY, the critical-path kernel of the main stream always enqueued first.
+        lane = _SideLane(self._side_stream() if self.side_wgrad and dx16.is_cuda else None, dx16.device)
         for i in reversed(range(a['depth'])):
             k = f"vit.{i}."
             (x0, mean1, rstd1, ln1, qkv, attn, lse, x1, mean2, rstd2, ln2, hpre, g) = st.blocks[i]
@@ -365,25 +379,26 @@ class CrullerEngine:
             def w_fc2(dx16=dx16, g=g, k=k):
                 ops.gemm(dx16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"),
                          bias_grad=ar.grad(k + "fc2.b"))
-            at_start = mark()           # dx16 of this block is complete here
+            at_start = lane.mark()      # dx16 of this block is complete here
             d_h = ops.gemm(dx16, ar.w16(k + "fc2.w"), b_mn=True, epi=EPI_DGELU_BF16, aux=hpre)
-            ev_fc2 = on_side(w_fc2, (dx16, g), after=at_start)      # main-stream kernel first: it is the critical path
+            ev_fc2 = lane.run(w_fc2, (dx16, g), after=at_start)
 
             def w_fc1(d_h=d_h, ln2=ln2, k=k):
                 ops.gemm(d_h, ln2, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"),
                          bias_grad=ar.grad(k + "fc1.b"))
+            at_dh = lane.mark()
             d_ln2 = ops.gemm(d_h, ar.w16(k + "fc1.w"), b_mn=True)
-            on_side(w_fc1, (d_h, ln2))
-            wait(ev_fc2)                # the LayerNorm backward below overwrites dx16
+            lane.run(w_fc1, (d_h, ln2), after=at_dh)
+            lane.wait(ev_fc2)           # the LayerNorm backward below overwrites dx16
             ops.layernorm_bwd(x1, mean2, rstd2, ar.w32(k + "n2.w"), ar.grad(k + "n2.w"), ar.grad(k + "n2.b"),
                               dy16=d_ln2, dres32=dx32, dx32=dx32, dx16=dx16)
             # --- attention
             def w_proj(dx16=dx16, attn=attn, k=k):
                 ops.gemm(dx16, attn, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "proj.w"),
                          bias_grad=ar.grad(k + "proj.b"))
-            at_ln2 = mark()
+            at_ln2 = lane.mark()
             d_attn = ops.gemm(dx16, ar.w16(k + "proj.w"), b_mn=True)
-            ev_proj = on_side(w_proj, (dx16, attn), after=at_ln2)
+            ev_proj = lane.run(w_proj, (dx16, attn), after=at_ln2)
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv, qkv, qkv, attn, d_attn, lse, dqkv, dqkv, dqkv, B=B, H=Hh, Sq=S, Sk=S,
                               q_col0=0, k_col0=D, v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D)
@@ -391,18 +406,17 @@ class CrullerEngine:
             def w_qkv(dqkv=dqkv, ln1=ln1, k=k):
                 ops.gemm(dqkv, ln1, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "qkv.w"),
                          bias_grad=ar.grad(k + "qkv.b"))
+            at_dqkv = lane.mark()
             d_ln1 = ops.gemm(dqkv, ar.w16(k + "qkv.w"), b_mn=True)
-            on_side(w_qkv, (dqkv, ln1))
-            wait(ev_proj)               # dx16 is overwritten again
+            lane.run(w_qkv, (dqkv, ln1), after=at_dqkv)
+            lane.wait(ev_proj)          # dx16 is overwritten again
             ops.layernorm_bwd(x0, mean1, rstd1, ar.w32(k + "n1.w"), ar.grad(k + "n1.w"), ar.grad(k + "n1.b"),
                               dy16=d_ln1, dres32=dx32, dx32=dx32, dx16=dx16)
             st.blocks[i] = None
             if self._grad_ready_hook is not None:
-                if side is not None:
-                    main.wait_stream(side)      # the all-reduce of this block's range must see its weight gradients
+                lane.join()             # the exchange of this block's range must see its weight gradients
                 self._grad_ready_hook(k + "n1.w", k + "fc2.b")
-        if side is not None:
-            main.wait_stream(side)
+        lane.join()
         if a['pre_norm']:
             xp, mean, rstd = st.pre
             ops.layernorm_bwd(xp, mean, rstd, ar.w32("vit.norm_pre.w"), ar.grad("vit.norm_pre.w"),
@@ -565,6 +579,8 @@ class CrullerEngine:
             dy32 = None
         ops.gemm(dlogits, st.h_last16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad("dec.tok"), M=V)
         d_enc32 = None
+        # weight / bias gradients behind the kernel that produces their dY, on the side stream (see encoder_backward)
+        lane = _SideLane(self._side_stream() if self.side_wgrad and dlogits.is_cuda else None, dlogits.device)
         for j in reversed(range(nl)):
             k = f"dec.{j}."
             (h0_16, qkv, a_s, lse_s, u1, m1, r1, h1_16, qc, kvc, a_c, lse_c, u2, m2, r2, h2_16, hpre, g, u3, m3,
@@ -573,50 +589,65 @@ class CrullerEngine:
             # du16 carries the mask of the sub-layer output that was dropped before the residual add (du32 does not)
             du32, du16 = ops.layernorm_bwd(u3, m3, r3, ar.w32(k + "f_ln.w"), ar.grad(k + "f_ln.w"),
                                            ar.grad(k + "f_ln.b"), dy16=dy16, dy32=dy32, out_drop=dr.site(j, 5))
+            at = lane.mark()
             d_h = ops.gemm(du16, ar.w16(k + "fc2.w"), b_mn=True, epi=EPI_DGELU_BF16, aux=hpre, drop=dr.site(j, 4))
-            ops.gemm(du16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"),
-                     bias_grad=ar.grad(k + "fc2.b"))
+            ev_du = lane.run(lambda du16=du16, g=g, k=k: ops.gemm(
+                du16, g, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc2.w"),
+                bias_grad=ar.grad(k + "fc2.b")), (du16, g), after=at)
+            at = lane.mark()
             d_h2 = ops.gemm(d_h, ar.w16(k + "fc1.w"), b_mn=True)
-            ops.gemm(d_h, h2_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"),
-                     bias_grad=ar.grad(k + "fc1.b"))
+            lane.run(lambda d_h=d_h, h2_16=h2_16, k=k: ops.gemm(
+                d_h, h2_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "fc1.w"),
+                bias_grad=ar.grad(k + "fc1.b")), (d_h, h2_16), after=at)
+            lane.wait(ev_du)            # the LayerNorm backward below overwrites du16
             # cross-attention LN
             du32, du16 = ops.layernorm_bwd(u2, m2, r2, ar.w32(k + "ca_ln.w"), ar.grad(k + "ca_ln.w"),
                                            ar.grad(k + "ca_ln.b"), dy16=d_h2, dy32=du32, dx32=du32, dx16=du16,
                                            out_drop=dr.site(j, 3))
+            at = lane.mark()
             d_ac = ops.gemm(du16, ar.w16(k + "ca.o.w"), b_mn=True)
-            ops.gemm(du16, a_c, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.o.w"),
-                     bias_grad=ar.grad(k + "ca.o.b"))
+            ev_du = lane.run(lambda du16=du16, a_c=a_c, k=k: ops.gemm(
+                du16, a_c, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.o.w"),
+                bias_grad=ar.grad(k + "ca.o.b")), (du16, a_c), after=at)
             dqc = torch.empty_like(qc)
             dkvc = torch.empty_like(kvc)
             ops.attention_bwd(qc, kvc, kvc, a_c, d_ac, lse_c, dqc, dkvc, dkvc, B=B, H=Hh, Sq=T, Sk=S, q_col0=0,
                               k_col0=0, v_col0=D, dq_col0=0, dk_col0=0, dv_col0=D, drop=dr.site(j, 2))
+            at = lane.mark()
             d_h1 = ops.gemm(dqc, ar.w16(k + "ca.q.w"), b_mn=True)
-            ops.gemm(dqc, h1_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.q.w"),
-                     bias_grad=ar.grad(k + "ca.q.b"))
+            lane.run(lambda dqc=dqc, h1_16=h1_16, k=k: ops.gemm(
+                dqc, h1_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "ca.q.w"),
+                bias_grad=ar.grad(k + "ca.q.b")), (dqc, h1_16), after=at)
             wkv = ar.span(k + "ca.k.w", k + "ca.v.w", "w16").view(2 * D, D)
             if d_enc32 is None:
                 d_enc32 = ops.gemm(dkvc, wkv, b_mn=True, epi=EPI_STORE_F32)
             else:
                 ops.gemm(dkvc, wkv, b_mn=True, epi=EPI_RESID_F32, aux=d_enc32, out=d_enc32)
-            ops.gemm(dkvc, enc16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
-                     out=ar.span(k + "ca.k.w", k + "ca.v.w", "grad").view(2 * D, D),
-                     bias_grad=ar.span(k + "ca.k.b", k + "ca.v.b", "grad"))
+            lane.run(lambda dkvc=dkvc, k=k: ops.gemm(
+                dkvc, enc16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
+                out=ar.span(k + "ca.k.w", k + "ca.v.w", "grad").view(2 * D, D),
+                bias_grad=ar.span(k + "ca.k.b", k + "ca.v.b", "grad")), (dkvc, enc16), after=at)
+            lane.wait(ev_du)            # du16 is overwritten again
             # self-attention LN
             du32, du16 = ops.layernorm_bwd(u1, m1, r1, ar.w32(k + "sa_ln.w"), ar.grad(k + "sa_ln.w"),
                                            ar.grad(k + "sa_ln.b"), dy16=d_h1, dy32=du32, dx32=du32, dx16=du16,
                                            out_drop=dr.site(j, 1))
+            at = lane.mark()
             d_as = ops.gemm(du16, ar.w16(k + "sa.o.w"), b_mn=True)
-            ops.gemm(du16, a_s, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "sa.o.w"),
-                     bias_grad=ar.grad(k + "sa.o.b"))
+            lane.run(lambda du16=du16, a_s=a_s, k=k: ops.gemm(
+                du16, a_s, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32, out=ar.grad(k + "sa.o.w"),
+                bias_grad=ar.grad(k + "sa.o.b")), (du16, a_s), after=at)
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv, qkv, qkv, a_s, d_as, lse_s, dqkv, dqkv, dqkv, B=B, H=Hh, Sq=T, Sk=T, q_col0=0,
                               k_col0=D, v_col0=2 * D, dq_col0=0, dk_col0=D, dv_col0=2 * D, causal=True,
                               drop=dr.site(j, 0))
             wqkv = ar.span(k + "sa.q.w", k + "sa.v.w", "w16").view(3 * D, D)
+            at = lane.mark()
             dy16 = ops.gemm(dqkv, wqkv, b_mn=True)
-            ops.gemm(dqkv, h0_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
-                     out=ar.span(k + "sa.q.w", k + "sa.v.w", "grad").view(3 * D, D),
-                     bias_grad=ar.span(k + "sa.q.b", k + "sa.v.b", "grad"))
+            lane.run(lambda dqkv=dqkv, h0_16=h0_16, k=k: ops.gemm(
+                dqkv, h0_16, a_mn=True, b_mn=True, epi=EPI_REDUCE_F32,
+                out=ar.span(k + "sa.q.w", k + "sa.v.w", "grad").view(3 * D, D),
+                bias_grad=ar.span(k + "sa.q.b", k + "sa.v.b", "grad")), (dqkv, h0_16), after=at)
             dy32 = du32
             st.layers[j] = None
         x_emb, me, re_ = st.emb
@@ -625,6 +656,7 @@ class CrullerEngine:
                                       in_drop=dr.emb())
         ops.embed_bwd(st.ids, dx_emb, ar.grad("dec.tok"), ar.grad("dec.pos"), pos_offset=2, scale=1.0,
                       padding_idx=cfg.pad_token_id)
+        lane.join()
         if self._grad_ready_hook is not None:
             self._grad_ready_hook("dec.tok", f"dec.{nl - 1}.f_ln.b")
         return d_enc32

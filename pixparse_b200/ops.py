@@ -4,6 +4,8 @@ Every function enqueues on torch's current CUDA stream and returns immediately. 
 contiguous in their last dimension; outputs are allocated by the caller or here through torch's
 caching allocator (the kernels never allocate).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -17,6 +19,34 @@ F32 = torch.float32
 def _ld(t):
     assert t.dim() == 2 and t.stride(1) == 1, "expected a 2-D tensor with unit inner stride"
     return t.stride(0)
+
+
+# Dynamic tile scheduling of the persistent GEMM grids (B200GemmArgs.tile_counter): every launch gets the next of a pool of
+# zero-initialised device counters (a counter is back at zero when its kernel ends, and 2048 launches later nothing of
+# that kernel is in flight), so kernels on different streams share the SMs work-conservingly. Opt-in
+# (PIXPARSE_B200_DYN_SCHED=1, with PIXPARSE_B200_SIDE_WGRAD=1 for the second stream): results are identical either way and,
+# measured on the headline step, so is the speed (profiles/r02_experiments_no_gain.txt).
+_DYN_SCHED = os.environ.get("PIXPARSE_B200_DYN_SCHED", "0") == "1"
+_SCHED_POOL = 2048
+_sched_pools = {}
+
+
+def set_dynamic_tiles(on):
+    """Switch the GEMM's dynamic tile scheduler on / off; returns the previous setting."""
+    global _DYN_SCHED
+    prev, _DYN_SCHED = _DYN_SCHED, bool(on)
+    return prev
+
+
+def _tile_counter(device):
+    if not _DYN_SCHED or torch.cuda.is_current_stream_capturing():
+        return None
+    st = _sched_pools.get(device)
+    if st is None:
+        st = _sched_pools[device] = [torch.zeros(_SCHED_POOL, device=device, dtype=torch.int32), 0]
+    i = st[1]
+    st[1] = (i + 1) % _SCHED_POOL
+    return st[0].data_ptr() + 4 * i
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=None, bias=None, aux=None,
@@ -51,7 +81,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=Non
                          b_mn_major=int(b_mn), m=M, n=N, k=K, out=ptr(out), ldo=_ld(out), out2=ptr(out2),
                          ldo2=_ld(out2) if out2 is not None else 0, bias=ptr(bias), aux=ptr(aux),
                          ld_aux=_ld(aux) if aux is not None else 0, bias_grad=ptr(bias_grad), splits=splits,
-                         block_n=block_n, drop_p=float(p), drop_seed=int(seed))
+                         block_n=block_n, drop_p=float(p), drop_seed=int(seed), tile_counter=_tile_counter(a.device))
     call("b200_gemm_bf16", args, stream())
     return out
 

@@ -73,7 +73,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
-    assert lib.b200_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.b200_abi_version() == _lib.ABI_VERSION == 3
     m = re.search(r"#define B200_ABI_VERSION (\d+)", open(HEADER).read())
     assert int(m.group(1)) == _lib.ABI_VERSION
 

@@ -93,6 +93,45 @@ def test_tiny_model_forward_backward_parity(cuda_lib, name, B, Lt):
     assert not bad, bad[:10]
 
 
+@pytest.mark.parametrize("name,B,Lt", [("cruller_test", 3, 130), ("cruller_base", 2, 513)])
+def test_side_stream_wgrad_with_dynamic_tiles_matches_static_single_stream(cuda_lib, name, B, Lt):
+    """Weight / bias gradients on the side stream + the GEMM's dynamic tile scheduler (the default) against the static
+    deal on one stream: same loss, same gradients; twice in a row, so that a tile counter left non-zero by the first
+    pass would show. Two runs of the SAME configuration already differ at the bf16-rounding level (the fp32 reduce-adds
+    of attention dQ and of the split-K weight gradients land in arbitrary order, and a last-bit difference can flip a
+    bf16 rounding downstream), hence rel-L2 1e-2 per tensor -- a lost or doubled work item is off by one tile's
+    worth, tens of percent."""
+    from pixparse_b200 import ops
+    from pixparse_b200.engine import engine_for
+    vocab = 50267
+    _, ours = _build_pair(name, vocab)
+    image, text, target = _batch(name, B, Lt)
+    eng = engine_for(ours)
+    results = []
+    prev_dyn, prev_side = ops.set_dynamic_tiles(False), eng.side_wgrad
+    try:
+        for dyn, side, reps in ((False, False, 1), (True, True, 2), (True, False, 1)):
+            ops.set_dynamic_tiles(dyn)
+            eng.side_wgrad = side
+            for _ in range(reps):
+                eng.zero_grads()
+                stats = eng.forward_backward(image, text[:, :-1].contiguous(), target[:, 1:].contiguous())
+                torch.cuda.synchronize()
+                results.append((stats[1].item(), {n: p.grad.clone() for n, p in ours.named_parameters()}))
+    finally:
+        ops.set_dynamic_tiles(prev_dyn)
+        eng.side_wgrad = prev_side
+    loss0, g0 = results[0]
+    total = torch.sqrt(sum((g.float() ** 2).sum() for g in g0.values())).item()
+    for loss, g in results[1:]:
+        assert abs(loss - loss0) <= 1e-6 * abs(loss0)
+        for n in g0:
+            if n.endswith("k_proj.bias"):       # true gradient is zero (softmax shift invariance): rounding noise only
+                continue
+            d = (g[n].float() - g0[n].float()).norm().item()
+            assert d <= 1e-2 * g0[n].float().norm().item() + 1e-5 * total, (n, d, g0[n].float().norm().item())
+
+
 def test_compat_autograd_path_matches_fused_path(cuda_lib):
     """Reference-literal usage: logits -> nn.CrossEntropyLoss -> loss.backward() -> param.grad."""
     from pixparse_b200.engine import engine_for
