@@ -89,8 +89,17 @@ typedef struct B200GemmArgs {
    * identical; what changes is that kernels sharing the GPU across streams split its SMs work-conservingly (a weight
    * gradient on a side stream fills the partly empty last wave of the main stream's kernel). */
   unsigned int* tile_counter;
+  /* Tail split (STORE_BF16 / RESID_F32, static tile deal). When the tiles do not fill the persistent grid's last wave
+   * (N = 768 outputs of the train step: 381 tiles on 74 CTA pairs = 5.15 waves) the tiles of that wave are cut along K
+   * into one piece per CTA that would otherwise idle; the pieces sum their fp32 accumulators in this workspace and the
+   * last piece to arrive runs the epilogue. Caller-owned, 128-byte aligned, ZERO on entry (the kernel leaves it zero), at
+   * least b200_gemm_tail_workspace_bytes() for every shape; launches sharing it must not overlap in time. NULL = off;
+   * also off unless b200_debug_gemm_tail_split(1) was called (opt-in, see there). */
+  void* tail_workspace;
+  long long tail_workspace_bytes;
 } B200GemmArgs;
 int b200_gemm_bf16(const B200GemmArgs* args, void* stream);
+long long b200_gemm_tail_workspace_bytes(void);
 
 /* ---- attention (tcgen05, flash-style, head_dim 64) ---------------------------------------------
  * q/k/v are [B, S, row] bf16 activations with `ld*` elements between tokens and `*_bstride` elements between batches
@@ -387,6 +396,9 @@ int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo, int b_sbo,
 /* Bring-up / A-B switch: on = 1 makes b200_gemm_bf16 use one CTA per 128-row tile everywhere instead of CTA pairs
  * (tcgen05 cta_group::2, 256-row tiles) for the 256-column tile width. Results are identical either way. */
 int b200_debug_gemm_single_cta(int on);
+/* Opt-in switch of the tail split: on = 1 lets b200_gemm_bf16 use B200GemmArgs.tail_workspace. Default 0 (measured
+ * slower on the train step's shapes: the fix-up costs more than the idle last wave it removes). */
+int b200_debug_gemm_tail_split(int on);
 /* Kernel selection for b200_attention_bwd without dropout: on = 1 (default) query-major accumulators (the kernel the
  * dropout variant always uses), on = 0 key-major accumulators (P^T / dS^T fed to the dV / dK MMAs from tensor memory).
  * Results agree to bf16 rounding; the two are on par on B200 (profiles/), the switch exists for A-B runs. */

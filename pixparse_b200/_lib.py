@@ -68,7 +68,7 @@ class GemmArgs(_Args):
     _fields_ = [("struct_size", _U), ("epilogue", _I), ("a", _P), ("lda", _L), ("a_mn_major", _I), ("b", _P), ("ldb", _L),
                 ("b_mn_major", _I), ("m", _I), ("n", _I), ("k", _I), ("out", _P), ("ldo", _L), ("out2", _P), ("ldo2", _L),
                 ("bias", _P), ("aux", _P), ("ld_aux", _L), ("bias_grad", _P), ("splits", _I), ("block_n", _I),
-                ("drop_p", _F), ("drop_seed", _U), ("tile_counter", _P)]
+                ("drop_p", _F), ("drop_seed", _U), ("tile_counter", _P), ("tail_workspace", _P), ("tail_workspace_bytes", _L)]
 
 
 class AttentionFwdArgs(_Args):
@@ -131,6 +131,7 @@ SIGNATURES = {
     "b200_device_check": [],
     "b200_debug_gemm_desc": [_I, _I, _I, _I, _I, _I],
     "b200_debug_gemm_single_cta": [_I],
+    "b200_debug_gemm_tail_split": [_I],
     "b200_debug_attention_bwd_query_major": [_I],
     "b200_gemm_bf16": [ctypes.POINTER(GemmArgs), _P],
     "b200_attention_fwd": [ctypes.POINTER(AttentionFwdArgs), _P],
@@ -160,9 +161,9 @@ SIGNATURES = {
 }
 # entry points whose return type is not int
 RESTYPES = {"b200_last_error": ctypes.c_char_p, "b200_attention_bwd_workspace_bytes": ctypes.c_longlong,
-            "b200_preprocess_workspace_bytes": ctypes.c_longlong}
+            "b200_preprocess_workspace_bytes": ctypes.c_longlong, "b200_gemm_tail_workspace_bytes": ctypes.c_longlong}
 OTHER_SIGNATURES = {"b200_last_error": [], "b200_attention_bwd_workspace_bytes": [_I, _I, _I],
-                    "b200_preprocess_workspace_bytes": [_I, _I]}
+                    "b200_preprocess_workspace_bytes": [_I, _I], "b200_gemm_tail_workspace_bytes": []}
 
 
 def _declare(l):

@@ -120,6 +120,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// orders accesses made through the async proxy (TMA, bulk reduce-adds) with generic-proxy accesses, all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -440,6 +444,11 @@ __device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ void sts32_cluster(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.volatile.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// fire-and-forget fp32 vector add into global memory (performed at L2), 16-byte aligned
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;

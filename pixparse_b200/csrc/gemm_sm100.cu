@@ -50,11 +50,18 @@ struct GemmParams {
   // dynamic tile scheduler: work items are handed out through this device counter (zero on entry, left at zero) instead
   // of the static round-robin deal; nullptr = static. See TileSched.
   unsigned int* tile_counter;
+  // Tail split (STORE_BF16 / RESID_F32 through the TMA epilogue, static deal): the tiles of the partly empty last wave are
+  // cut into tail_splits pieces of tail_kb k-blocks so that the wave is full; see the epilogue. tail_splits = 1: off.
+  int full_tiles, tail_splits, tail_kb;
+  float* tail_ws;              // fp32 partial sums, [tail tile][tile rows][BN], zero on entry and on exit
+  unsigned int* tail_count;    // arrivals per (tail tile, CTA of the pair, epilogue group), zero on entry and on exit
 };
 
 // debug override of the descriptor parameters (used only by the bring-up script; -1 = default)
 static int g_desc_override[6] = {-1, -1, -1, -1, -1, -1};
 static int g_force_single_cta = 0;      // bring-up / A-B switch: 1 = never use CTA pairs
+static int g_tail_split = 0;            // opt-in (b200_debug_gemm_tail_split): measured slower on the train step, see below
+constexpr long long TAIL_COUNTER_BYTES = 4096;      // head of the tail workspace: arrival counters (4 per tail tile)
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile; each CTA
 // stages its own 128 rows of A and BN / 2 rows of B, so a k-block costs 32 KB of L2 -> SM traffic per SM instead of 48.
@@ -73,7 +80,7 @@ struct GemmCfg {
   // under load) wherever the ring can spare the space
   static constexpr int NAUX = HAS_AUX ? (((CG == 2 || BN == 128) && !DEEP) ? 2 : 1) : 0;
   static constexpr int EPI_GROUP_BYTES = (1 + (EPI == B200_EPI_GELU_BF16 ? 1 : NAUX)) * EPI_BUF_BYTES;
-  static constexpr int TAIL_BYTES = 256 /* barriers */ + 1024 /* bias */ + 64 /* tile ring */ + 1024 /* alignment slack */;
+  static constexpr int TAIL_BYTES = 256 /* barriers */ + 1024 /* bias */ + 128 /* tile ring, tail flags */ + 1024 /* alignment slack */;
   static constexpr int MAX_STAGES = (232448 - TAIL_BYTES - 2 * EPI_GROUP_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES < 6 ? MAX_STAGES : 6;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (256 or 512 columns: powers of two)
@@ -133,10 +140,31 @@ struct TileSched {
   }
 };
 
-__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& n_tile, int& split) {
+// work item w -> output tile (m_tile, n_tile), k-block range [kb0, kb1) and, for a piece of a split tail tile, the index of
+// that tile among the tail tiles (-1: the item is a whole tile or an ordinary split-K item)
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& n_tile, int& kb0, int& kb1,
+                                            int& tail) {
   const int tiles = p.m_tiles * p.n_tiles;
-  split = w / tiles;
-  const int t = w - split * tiles;
+  int t;
+  tail = -1;
+  if (p.tail_splits > 1) {
+    if (w < p.full_tiles) {
+      t = w;
+      kb0 = 0;
+      kb1 = p.k_blocks;
+    } else {
+      const int j = w - p.full_tiles;
+      tail = j / p.tail_splits;
+      t = p.full_tiles + tail;
+      kb0 = (j - tail * p.tail_splits) * p.tail_kb;
+      kb1 = min(p.k_blocks, kb0 + p.tail_kb);
+    }
+  } else {
+    const int split = w / tiles;
+    t = w - split * tiles;
+    kb0 = split * p.kb_per_split;
+    kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+  }
   const int per_group = p.group_m * p.n_tiles;
   const int group = t / per_group;
   const int first_m = group * p.group_m;
@@ -302,7 +330,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmap_ws, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG, EPI, DEEP>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -371,7 +399,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // prologue done; operands / outputs of the predecessor kernel are touched only from here on
 
-  const int total_work = p.m_tiles * p.n_tiles * p.splits;
+  const int total_work = p.tail_splits > 1 ? p.full_tiles + (p.m_tiles * p.n_tiles - p.full_tiles) * p.tail_splits
+                                           : p.m_tiles * p.n_tiles * p.splits;
   const TileSched sched{smem_u32(sched_ring), worker, n_workers, total_work, p.tile_counter};
 
   if (warp == 8) {
@@ -387,11 +416,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int seq = 0;; ++seq) {
         const int w = sched.get(seq);
         if (w >= total_work) break;
-        int m_tile, n_tile, split;
-        decode_work(p, w, m_tile, n_tile, split);
+        int m_tile, n_tile, kb0, kb1, tail;
+        decode_work(p, w, m_tile, n_tile, kb0, kb1, tail);
         if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;      // this CTA's 128 rows of the pair's 256
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (CG == 2) {
@@ -457,10 +484,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int seq = 0;; ++seq) {
         const int w = sched.get(seq);
         if (w >= total_work) break;
-        int m_tile, n_tile, split;
-        decode_work(p, w, m_tile, n_tile, split);
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        int m_tile, n_tile, kb0, kb1, tail;
+        decode_work(p, w, m_tile, n_tile, kb0, kb1, tail);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -517,11 +542,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int seq = 0;; ++seq) {
       const int w = sched.get(seq);
       if (w >= total_work) break;
-      int m_tile, n_tile, split;
-      decode_work(p, w, m_tile, n_tile, split);
+      int m_tile, n_tile, kb0, kb1, tail;
+      decode_work(p, w, m_tile, n_tile, kb0, kb1, tail);
       if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
       int turn = kb0 % p.n_tiles;       // k-block kb belongs to the item with n_tile == kb % n_tiles
       // lane -> (row phase rq = lane / 8, 16-byte piece c16 = lane % 8): one LDS.128 covers four token rows of the
       // chunk (512 bytes, conflict-free), 16 of them per k-block; each lane keeps 8 feature sums for its row phase
@@ -619,8 +642,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         const int w = sched.get(wseq);
         if (w >= total_work) return;
-        int m_t, n_t, sp;
-        decode_work(p, w, m_t, n_t, sp);
+        int m_t, n_t, k0_, k1_, tl_;
+        decode_work(p, w, m_t, n_t, k0_, k1_, tl_);
         if (CG == 2) m_t = m_t * 2 + (int)cta_rank;
         const int slot = (int)(seq % NAUX);
         mbar_expect_tx(&aux_full_bar[2 * grp + slot], EPI_BUF_BYTES);
@@ -633,8 +656,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int wseq = 0;; ++wseq) {
         const int w = sched.get(wseq);
         if (w >= total_work) break;
-        int m_tile, n_tile, split;
-        decode_work(p, w, m_tile, n_tile, split);
+        int m_tile, n_tile, kb0_, kb1_, tail;
+        decode_work(p, w, m_tile, n_tile, kb0_, kb1_, tail);
         if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
         if (p.bias != nullptr) {
           if (et < BN / 2) {
@@ -647,6 +670,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
         const int grow = m_tile * BM + row_in_tile;
+        // ---- tail split. 381 tiles on 74 CTA pairs are 5.15 waves: the last wave keeps 11 pairs busy for a whole tile while
+        // 63 idle (14 % of the kernel at N = 768). The host cuts the tiles of such a wave along K into tail_splits pieces, one
+        // per otherwise idle worker (a piece is always its worker's last item). Every piece adds its fp32 accumulator into
+        // the tile's workspace area (TMA reduce-add, as the weight gradients do) and then draws an arrival ticket for its
+        // (tile, CTA of the pair, epilogue group); whoever draws the last one runs the ordinary epilogue below with the
+        // summed tile read back from the workspace (L2) instead of tensor memory, and leaves workspace and counter
+        // zeroed for the next launch. Nobody waits for anybody.
+        const float* ws_row = nullptr;     // non-null: this thread's row of the summed tile (last arriver of a split tile)
+        if (tail >= 0) {
+          const int ws_r0 = (tail * CG + (int)cta_rank) * BM;      // first workspace row of this CTA's 128 tile rows
+          float* ws_mine = p.tail_ws + (long long)(ws_r0 + row_in_tile) * BN;
+          // (the same columns this group owns in the epilogue proper: rounds of CW columns, 32 at a time, staged in the
+          // swizzled layout and added by the TMA unit. Per-thread vector reds -- red.global.add.v4.f32 straight from the
+          // accumulator rows -- were measured 25 us per GEMM slower: the L2 atomic units take them a scalar at a time.)
+#pragma unroll 1
+          for (int ch = 0; ch < ROUNDS * HALVES; ++ch) {
+            const int col = (grp + 2 * (ch / HALVES)) * CW + 32 * (ch % HALVES);
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + col, r);
+            tmem_ld_wait();
+            if (ch == ROUNDS * HALVES - 1) {      // last TMEM read of this accumulator stage: hand it back
+              tc_fence_before();
+              if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            if (et == 0) tma_wait_group_read<0>();      // the staging tile is free (earlier bulk stores / reduce-adds have read it)
+            named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts128(rowp + ((j ^ swz) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, 128);
+            if (et == 0) {
+              tma_reduce_add_2d(&tmap_ws, buf, col, ws_r0);
+              tma_commit_group();
+            }
+          }
+          uint32_t* last_flag = sched_ring + SCHED_RING + grp;
+          if (et == 0) {
+            tma_wait_group<0>();               // this group's reduce-adds are performed ...
+            fence_proxy_async_all();
+            __threadfence();                   // ... and ordered before the ticket
+            unsigned int* cnt = p.tail_count + (tail * 2 + (int)cta_rank) * 2 + grp;
+            const unsigned int ticket = atomicAdd(cnt, 1u);
+            const bool last = ticket == (unsigned int)(p.tail_splits - 1);
+            if (last) {
+              atomicExch(cnt, 0u);
+              __threadfence();
+            }
+            *last_flag = last ? 1u : 0u;
+          }
+          named_bar_sync(bar_id, 128);
+          const bool last = *reinterpret_cast<volatile uint32_t*>(last_flag) != 0u;
+          if (!last) {
+            // the aux tiles prefetched for this item are not consumed: let them land before the CTA can exit
+            if (AUX && et == 0)
+              for (int a = 0; a < NAUX; ++a)
+                mbar_wait(&aux_full_bar[2 * grp + (int)((aux_seq + a) % NAUX)], ((aux_seq + a) / NAUX) & 1u);
+            continue;                          // (a tail piece is the worker's last item)
+          }
+          ws_row = ws_mine;
+        }
 #pragma unroll 1
         for (int rd = 0; rd < ROUNDS; ++rd) {
           const int cc = (grp + 2 * rd) * CW;        // first column of the round inside the tile
@@ -656,7 +740,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll 1      // (rolled: the unrolled round was 670 instructions, and 6 % of the epilogue's samples were i-cache misses)
           for (int hf = 0; hf < HALVES; ++hf) {
             uint32_t r[32];
-            tmem_ld_32x32(taddr + cc + 32 * hf, r);
+            if (ws_row != nullptr) {
+              // summed tile of a split tail tile: 128 contiguous bytes of this thread's workspace row, zeroed behind the read
+              float4* src = reinterpret_cast<float4*>(const_cast<float*>(ws_row) + cc + 32 * hf);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t4 = __ldcg(src + j);
+                r[4 * j] = __float_as_uint(t4.x); r[4 * j + 1] = __float_as_uint(t4.y);
+                r[4 * j + 2] = __float_as_uint(t4.z); r[4 * j + 3] = __float_as_uint(t4.w);
+                __stcg(src + j, make_float4(0.f, 0.f, 0.f, 0.f));
+              }
+            } else {
+              tmem_ld_32x32(taddr + cc + 32 * hf, r);
+            }
             // aux of these 32 columns: 32 bf16 = 4 pieces (DGELU) or 32 fp32 = 8 pieces (RESID)
             constexpr int AXP = OUT_F32 ? 8 : 4;
             uint32_t ax[AUX ? 4 * AXP : 1];
@@ -666,7 +762,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 const uint4 t4 = lds128(row2p + aslot * EPI_BUF_BYTES + (((AXP * hf + j) ^ swz) << 4));
                 ax[AUX ? 4 * j : 0] = t4.x; ax[AUX ? 4 * j + 1 : 0] = t4.y; ax[AUX ? 4 * j + 2 : 0] = t4.z; ax[AUX ? 4 * j + 3 : 0] = t4.w;
               }
-              if (hf == HALVES - 1) {
+              // Release the aux tile right behind the reads -- except on the workspace route: there 16 global loads / stores
+              // per thread sit in the memory pipe in front of these shared-memory reads, the barrier arrive overtakes them,
+              // and the refill lands in rows that have not been read yet (seen on the GPU: the last two pieces of some
+              // rows came from the NEXT round's columns). That route releases after the arithmetic has consumed ax[].
+              if (hf == HALVES - 1 && ws_row == nullptr) {
                 mbar_arrive(&aux_free_bar[2 * grp + aslot]);
                 if (et == 0) {
                   // refill this aux tile for the round NAUX rounds ahead (possibly of a later tile) once all have read it
@@ -677,7 +777,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
             tmem_ld_wait();
-            if (rd == ROUNDS - 1 && hf == HALVES - 1) {   // last TMEM read of this accumulator stage: hand it back
+            if (ws_row == nullptr && rd == ROUNDS - 1 && hf == HALVES - 1) {   // last TMEM read of this accumulator stage: hand it back
               tc_fence_before();
               if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
               else mbar_arrive(&tmem_empty_bar[acc]);
@@ -747,6 +847,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 o[OUT_F32 ? 4 * q + 3 : 0] = __float_as_uint(v3);
               }
             }
+            if (AUX && hf == HALVES - 1 && ws_row != nullptr) {      // (see above: ax[] is in registers and consumed by now)
+              mbar_arrive(&aux_free_bar[2 * grp + aslot]);
+              if (et == 0) {
+                mbar_wait(&aux_free_bar[2 * grp + aslot], aphase);
+                issue_aux(wseq, rd, NAUX, aux_seq);
+              }
+              ++aux_seq;
+            }
             if (hf == 0) {
               // the staging tile(s) must be free: the previous round's bulk store has finished reading them
               if (et == 0) tma_wait_group_read<0>();
@@ -779,8 +887,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int wseq = 0;; ++wseq) {
       const int w = sched.get(wseq);
       if (w >= total_work) break;
-      int m_tile, n_tile, split;
-      decode_work(p, w, m_tile, n_tile, split);
+      int m_tile, n_tile, kb0_, kb1_, tail_;
+      decode_work(p, w, m_tile, n_tile, kb0_, kb1_, tail_);
       if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -853,7 +961,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // host side
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = false>
-static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tws,
                           const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG, DROP, DEEP>;
   constexpr int SMEM = GemmCfg<BN, CG, EPI, DEEP>::SMEM_BYTES;
@@ -863,7 +971,7 @@ static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm)");
     configured = true;
   }
-  cudaError_t e = launch_kernel(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), SMEM, stream, CG, ta, tb, to, to2, p);
+  cudaError_t e = launch_kernel(kern, dim3((unsigned)grid), dim3(GEMM_THREADS), SMEM, stream, CG, ta, tb, to, to2, tws, p);
   if (e != cudaSuccess) return check_cuda(e, "gemm_kernel launch");
   B200_CHECK_LAUNCH("gemm_kernel launch");
   return 0;
@@ -871,7 +979,7 @@ static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 
 // p.m_tiles counts 256-row pair tiles when cta_pairs is set (BN = 256 only)
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tws,
                        const GemmParams& p, int grid, bool cta_pairs, cudaStream_t stream) {
   constexpr bool CAN_DROP = EPI == B200_EPI_RESID_F32 || EPI == B200_EPI_GELU_BF16 || EPI == B200_EPI_DGELU_BF16;
   // fc2 + residual of the forward pass (K-major operands, K >= 2048): the deeper operand ring (GemmCfg DEEP)
@@ -879,27 +987,27 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const bool deep = HAS_DEEP && p.K >= 2048;
   if (CAN_DROP && p.drop_threshold16 != 0u) {
     if (BN == 256 && cta_pairs) {
-      if (deep) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP, HAS_DEEP>(ta, tb, to, to2, p, grid, stream);
-      return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP>(ta, tb, to, to2, p, grid, stream);
+      if (deep) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP, HAS_DEEP>(ta, tb, to, to2, tws, p, grid, stream);
+      return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP>(ta, tb, to, to2, tws, p, grid, stream);
     }
-    return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, CAN_DROP>(ta, tb, to, to2, p, grid, stream);
+    return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, CAN_DROP>(ta, tb, to, to2, tws, p, grid, stream);
   }
   if (BN == 256 && cta_pairs && deep)
-    return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false, HAS_DEEP>(ta, tb, to, to2, p, grid, stream);
-  if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false>(ta, tb, to, to2, p, grid, stream);
-  return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, false>(ta, tb, to, to2, p, grid, stream);
+    return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false, HAS_DEEP>(ta, tb, to, to2, tws, p, grid, stream);
+  if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false>(ta, tb, to, to2, tws, p, grid, stream);
+  return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, false>(ta, tb, to, to2, tws, p, grid, stream);
 }
 
 template <int BN, bool A_MN, bool B_MN>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
-                        const CUtensorMap& to2, const GemmParams& p, int grid, bool pairs, cudaStream_t s) {
+                        const CUtensorMap& to2, const CUtensorMap& tws, const GemmParams& p, int grid, bool pairs, cudaStream_t s) {
   switch (epi) {
-    case B200_EPI_STORE_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_BF16>(ta, tb, to, to2, p, grid, pairs, s);
-    case B200_EPI_GELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_GELU_BF16>(ta, tb, to, to2, p, grid, pairs, s);
-    case B200_EPI_RESID_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_RESID_F32>(ta, tb, to, to2, p, grid, pairs, s);
-    case B200_EPI_DGELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_DGELU_BF16>(ta, tb, to, to2, p, grid, pairs, s);
-    case B200_EPI_REDUCE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_REDUCE_F32>(ta, tb, to, to2, p, grid, pairs, s);
-    case B200_EPI_STORE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_F32>(ta, tb, to, to2, p, grid, pairs, s);
+    case B200_EPI_STORE_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_BF16>(ta, tb, to, to2, tws, p, grid, pairs, s);
+    case B200_EPI_GELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_GELU_BF16>(ta, tb, to, to2, tws, p, grid, pairs, s);
+    case B200_EPI_RESID_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_RESID_F32>(ta, tb, to, to2, tws, p, grid, pairs, s);
+    case B200_EPI_DGELU_BF16: return launch_gemm<BN, A_MN, B_MN, B200_EPI_DGELU_BF16>(ta, tb, to, to2, tws, p, grid, pairs, s);
+    case B200_EPI_REDUCE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_REDUCE_F32>(ta, tb, to, to2, tws, p, grid, pairs, s);
+    case B200_EPI_STORE_F32: return launch_gemm<BN, A_MN, B_MN, B200_EPI_STORE_F32>(ta, tb, to, to2, tws, p, grid, pairs, s);
   }
   set_last_error("b200_gemm_bf16: unknown epilogue %d", epi);
   return -1;
@@ -918,6 +1026,16 @@ extern "C" int b200_debug_gemm_desc(int a_lbo, int a_sbo, int a_kadv, int b_lbo,
 extern "C" int b200_debug_gemm_single_cta(int on) {
   g_force_single_cta = on;
   return 0;
+}
+
+extern "C" int b200_debug_gemm_tail_split(int on) {
+  g_tail_split = on;
+  return 0;
+}
+
+// bytes of B200GemmArgs.tail_workspace that cover every shape: counters + one fp32 tile per tile of a half-full last wave
+extern "C" long long b200_gemm_tail_workspace_bytes(void) {
+  return TAIL_COUNTER_BYTES + (long long)(num_sms() / 2) * BM * 256 * 4;
 }
 
 extern "C" int b200_gemm_bf16(const B200GemmArgs* args, void* stream_) {
@@ -994,6 +1112,8 @@ extern "C" int b200_gemm_bf16(const B200GemmArgs* args, void* stream_) {
   p.bias_grad = bias_grad;
   // dynamic tile scheduler (caller-owned, zero-initialised counter); items must fit the 20-bit field of a ring word
   p.tile_counter = ((long long)tiles * p.splits <= SCHED_MAX_ITEMS) ? args->tile_counter : nullptr;
+  B200_CHECK_ARG(args->tail_workspace == nullptr || (reinterpret_cast<uintptr_t>(args->tail_workspace) & 127) == 0,
+                 "b200_gemm_bf16: tail_workspace must be 128-byte aligned");
   if (bias_grad != nullptr)
     B200_CHECK_ARG(epilogue == B200_EPI_REDUCE_F32 && a_mn_major,
                    "b200_gemm_bf16: bias_grad is fused only into weight gradients (REDUCE_F32 epilogue, A MN-major)");
@@ -1021,9 +1141,11 @@ extern "C" int b200_gemm_bf16(const B200GemmArgs* args, void* stream_) {
   if (epilogue == B200_EPI_RESID_F32 || epilogue == B200_EPI_DGELU_BF16)
     B200_CHECK_ARG(aux != nullptr, "epilogue %d needs aux", epilogue);
 
-  CUtensorMap ta, tb, to, to2;
+  CUtensorMap ta, tb, to, to2, tws;
   memset(&to, 0, sizeof(to));
   memset(&to2, 0, sizeof(to2));
+  memset(&tws, 0, sizeof(tws));
+  p.full_tiles = tiles; p.tail_splits = 1; p.tail_kb = p.k_blocks; p.tail_ws = nullptr; p.tail_count = nullptr;
   int rc;
   {
     // A: K-major -> global [M rows][K cols]; MN-major -> global [K rows][M cols]
@@ -1088,17 +1210,46 @@ extern "C" int b200_gemm_bf16(const B200GemmArgs* args, void* stream_) {
       p.tma_epi = 1;
     }
   }
-  int grid = tiles * p.splits;
+  int work_items = tiles * p.splits;
+  // Tail split (see the epilogue): whole waves of tiles, then the tiles of the last, at most half-full wave cut along K into
+  // one piece per worker that would idle. Needs the TMA epilogue, the static deal (a piece must be its worker's last
+  // item), >= 8 k-blocks per piece and >= 32 k-blocks per tile. OPT-IN: parity-green, but measured on the train step
+  // (profiles/r02_experiments_no_gain.txt) the fix-up -- reduce-adds of 6 x 256 KB per tile, a device-wide ticket, the
+  // read-back -- costs more than the 5/6 of a 20 us tile it saves: the N = 768 dgrads got 12 us slower per call, not 10 us
+  // faster.
+  if ((epilogue == B200_EPI_STORE_BF16 || epilogue == B200_EPI_RESID_F32) && p.tma_epi && p.tile_counter == nullptr &&
+      args->tail_workspace != nullptr && g_tail_split && tiles > sms && p.k_blocks >= 32) {
+    const int tail = tiles % sms;
+    const long long tile_bytes = (long long)tile_m * BN * 4;
+    if (tail > 0 && 2 * tail <= sms && TAIL_COUNTER_BYTES + tail * tile_bytes <= args->tail_workspace_bytes) {
+      int s_try = sms / tail;
+      if (s_try > p.k_blocks / 8) s_try = p.k_blocks / 8;
+      if (s_try >= 2) {
+        p.tail_kb = (p.k_blocks + s_try - 1) / s_try;
+        p.tail_splits = (p.k_blocks + p.tail_kb - 1) / p.tail_kb;      // no empty pieces
+        p.full_tiles = tiles - tail;
+        p.tail_count = reinterpret_cast<unsigned int*>(args->tail_workspace);
+        p.tail_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(args->tail_workspace) + TAIL_COUNTER_BYTES);
+        work_items = p.full_tiles + tail * p.tail_splits;
+        uint64_t dims[2] = {(uint64_t)BN, (uint64_t)tail * tile_m};
+        uint64_t strides[1] = {(uint64_t)BN * 4};
+        uint32_t box[2] = {EPI_COLS, BM};
+        int rc = make_tmap(&tws, p.tail_ws, TMA_F32, 2, dims, strides, box, TMA_SWIZZLE_128B);
+        if (rc) return rc;
+      }
+    }
+  }
+  int grid = work_items;
   if (grid > sms) grid = sms;
   if (cta_pairs) grid *= 2;
 
   if (BN == 256) {
-    if (combo == 0) return dispatch_epi<256, false, false>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
-    if (combo == 1) return dispatch_epi<256, false, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
-    return dispatch_epi<256, true, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
+    if (combo == 0) return dispatch_epi<256, false, false>(epilogue, ta, tb, to, to2, tws, p, grid, cta_pairs, stream);
+    if (combo == 1) return dispatch_epi<256, false, true>(epilogue, ta, tb, to, to2, tws, p, grid, cta_pairs, stream);
+    return dispatch_epi<256, true, true>(epilogue, ta, tb, to, to2, tws, p, grid, cta_pairs, stream);
   } else {
-    if (combo == 0) return dispatch_epi<128, false, false>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
-    if (combo == 1) return dispatch_epi<128, false, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
-    return dispatch_epi<128, true, true>(epilogue, ta, tb, to, to2, p, grid, cta_pairs, stream);
+    if (combo == 0) return dispatch_epi<128, false, false>(epilogue, ta, tb, to, to2, tws, p, grid, cta_pairs, stream);
+    if (combo == 1) return dispatch_epi<128, false, true>(epilogue, ta, tb, to, to2, tws, p, grid, cta_pairs, stream);
+    return dispatch_epi<128, true, true>(epilogue, ta, tb, to, to2, tws, p, grid, cta_pairs, stream);
   }
 }

@@ -49,6 +49,36 @@ def _tile_counter(device):
     return st[0].data_ptr() + 4 * i
 
 
+# Workspace of the GEMM's tail split (B200GemmArgs.tail_workspace): one zero-initialised buffer per device and stream -- the
+# kernel leaves it zeroed, and launches that share it must not overlap in time, which stream order guarantees. Opt-in
+# (PIXPARSE_B200_GEMM_TAIL_SPLIT=1 / set_tail_split): parity-green but slower on the train step's shapes.
+_tail_ws = {}
+_TAIL_SPLIT = None
+
+
+def set_tail_split(on):
+    """Switch the GEMM's tail split on / off (library switch + workspace hand-over); returns the previous setting."""
+    global _TAIL_SPLIT
+    prev, _TAIL_SPLIT = bool(_TAIL_SPLIT), bool(on)
+    _lib.lib().b200_debug_gemm_tail_split(int(_TAIL_SPLIT))
+    return prev
+
+
+def _tail_workspace(device):
+    if _TAIL_SPLIT is None:
+        set_tail_split(os.environ.get("PIXPARSE_B200_GEMM_TAIL_SPLIT", "0") == "1")
+    if not _TAIL_SPLIT:
+        return None, 0
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _tail_ws.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None, 0
+        nbytes = _lib.lib().b200_gemm_tail_workspace_bytes()
+        ws = _tail_ws[key] = torch.zeros((nbytes + 3) // 4, device=device, dtype=torch.int32)
+    return ws, ws.numel() * 4
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=None, bias=None, aux=None,
          splits=0, block_n=0, M=None, N=None, K=None, drop=None, bias_grad=None):
     """D[M,N] = sum_k A(m,k) B(n,k) on the tcgen05 path.
@@ -77,11 +107,13 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epi=EPI_STORE_BF16, out=None, out2=Non
     if bias_grad is not None:
         assert bias_grad.dtype == F32 and bias_grad.numel() >= M
     p, seed = drop if (drop is not None and drop[0] > 0.0) else (0.0, 0)
+    tail_ws, tail_bytes = _tail_workspace(a.device) if epi in (EPI_STORE_BF16, EPI_RESID_F32) else (None, 0)
     args = _lib.GemmArgs(epilogue=epi, a=ptr(a), lda=_ld(a), a_mn_major=int(a_mn), b=ptr(b), ldb=_ld(b),
                          b_mn_major=int(b_mn), m=M, n=N, k=K, out=ptr(out), ldo=_ld(out), out2=ptr(out2),
                          ldo2=_ld(out2) if out2 is not None else 0, bias=ptr(bias), aux=ptr(aux),
                          ld_aux=_ld(aux) if aux is not None else 0, bias_grad=ptr(bias_grad), splits=splits,
-                         block_n=block_n, drop_p=float(p), drop_seed=int(seed), tile_counter=_tile_counter(a.device))
+                         block_n=block_n, drop_p=float(p), drop_seed=int(seed), tile_counter=_tile_counter(a.device),
+                         tail_workspace=ptr(tail_ws), tail_workspace_bytes=tail_bytes)
     call("b200_gemm_bf16", args, stream())
     return out
 

@@ -75,6 +75,63 @@ def _gemm_epilogues_case(M, N, K):
     assert rel_err(out, hf.grad) < 4e-3
 
 
+# Tail split (B200GemmArgs.tail_workspace): tiles that leave the persistent grid's last wave at most half full are cut along
+# K and summed through the workspace. On 74 CTA pairs: (6656, 768, 2048) = 78 pair tiles -> 4 tail tiles x 4 pieces;
+# (6700, 776, 2304) = ragged M / N, 108 tiles -> 34 tail tiles x 2 pieces; single-CTA tiles change the counts (156 / 212
+# tiles on 148 CTAs). Each case runs twice: the kernel must leave workspace and counters zeroed.
+@pytest.mark.parametrize("M,N,K", [(6656, 768, 2048), (6700, 776, 2304)])
+@pytest.mark.parametrize("single_cta", [0, 1])
+def test_gemm_tail_split(cuda_lib, M, N, K, single_cta):
+    from pixparse_b200 import ops, _lib
+    _lib.lib().b200_debug_gemm_single_cta(single_cta)
+    prev_split = ops.set_tail_split(True)       # opt-in feature
+    try:
+        torch.manual_seed(4)
+        A = torch.randn((M, K), device=DEV).bfloat16()
+        B = torch.randn((N, K), device=DEV).bfloat16()
+        Bt = B.t().contiguous() if N % 8 == 0 else None      # MN-major B (dgrad layout) needs a 16-byte row pitch
+        bias = torch.randn(N, device=DEV)
+        acc = A.float() @ B.float().t()
+        x0 = torch.randn((M, N), device=DEV)
+        for rep in range(2):
+            out = ops.gemm(A, B, epi=ops.EPI_STORE_BF16, bias=bias)
+            assert rel_err(out, acc + bias) < 4e-3, rep
+            if Bt is not None:
+                out = ops.gemm(A, Bt, b_mn=True, epi=ops.EPI_STORE_BF16)
+                assert rel_err(out, acc) < 4e-3, rep
+            x = x0.clone()
+            ops.gemm(A, B, epi=ops.EPI_RESID_F32, bias=bias, aux=x, out=x)      # K >= 2048: the deep-ring variant
+            assert rel_err(x, x0 + acc + bias) < 1e-5, rep
+            y = torch.empty_like(x0)
+            ops.gemm(A, B, epi=ops.EPI_RESID_F32, bias=bias, aux=x0, out=y, drop=(0.25, 1234 + rep))
+            kept = (y != x0)
+            frac = kept.float().mean().item()
+            assert abs(frac - 0.75) < 5e-3, frac
+            assert rel_err(y[kept], (x0 + (acc + bias) / 0.75)[kept]) < 1e-5
+        # the fix-up's ordering (pieces' reduce-adds -> ticket -> read-back by the last arriver; the aux tile released only
+        # after it was consumed) under repetition: a partial sum that is read too early, or lands after the workspace was
+        # zeroed, is off by a whole K piece (~20) against a tolerance of 1e-2
+        ref = x0 + acc + bias
+        y = torch.empty_like(x0)
+        worst = torch.zeros((), device=DEV)
+        for _ in range(40):
+            ops.gemm(A, B, epi=ops.EPI_RESID_F32, bias=bias, aux=x0, out=y)
+            worst = torch.maximum(worst, (y - ref).abs().max())
+        assert worst.item() < 1e-2, worst.item()
+        ws, _ = ops._tail_workspace(A.device)
+        torch.cuda.synchronize()
+        assert int(ws.count_nonzero().item()) == 0, "tail workspace / counters not left zeroed"
+        # and the switch: without the split the same call gives the same answer up to fp32 summation order
+        ops.set_tail_split(False)
+        ref = ops.gemm(A, B, epi=ops.EPI_STORE_BF16, bias=bias)
+        ops.set_tail_split(True)
+        out = ops.gemm(A, B, epi=ops.EPI_STORE_BF16, bias=bias)
+        assert (out.float() - ref.float()).abs().max().item() <= 2 ** -6 * ref.float().abs().max().item()
+    finally:
+        _lib.lib().b200_debug_gemm_single_cta(0)
+        ops.set_tail_split(prev_split)
+
+
 def test_gemm_splitk_reduce_accumulates(cuda_lib):
     from pixparse_b200 import ops
     torch.manual_seed(3)
