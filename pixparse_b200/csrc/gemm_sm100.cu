@@ -105,12 +105,15 @@ struct GemmCfg {
 constexpr int SCHED_RING = 16;
 constexpr int SCHED_MAX_ITEMS = (1 << 20) - 1;
 
+// (DYN is a kernel template parameter: the static kernels carry none of this -- the step's default path lost 0.5 % with the
+// polling code and the tail-split epilogue merely compiled in, the epilogues being instruction-cache sensitive)
+template <bool DYN>
 struct TileSched {
   uint32_t ring_s;          // shared address of this CTA's ring
   int worker, n_workers, total;
-  unsigned int* counter;    // nullptr = static
+  unsigned int* counter;    // dynamic only
 
-  __device__ __forceinline__ bool dynamic() const { return counter != nullptr; }
+  __device__ __forceinline__ bool dynamic() const { return DYN; }
   // the worker's seq-th work item (>= total: none left); dynamic: spins until the producer has published it
   __device__ __forceinline__ int get(int seq) const {
     if (!dynamic()) {
@@ -142,12 +145,13 @@ struct TileSched {
 
 // work item w -> output tile (m_tile, n_tile), k-block range [kb0, kb1) and, for a piece of a split tail tile, the index of
 // that tile among the tail tiles (-1: the item is a whole tile or an ordinary split-K item)
+template <bool TAIL>
 __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_tile, int& n_tile, int& kb0, int& kb1,
                                             int& tail) {
   const int tiles = p.m_tiles * p.n_tiles;
   int t;
   tail = -1;
-  if (p.tail_splits > 1) {
+  if (TAIL) {
     if (w < p.full_tiles) {
       t = w;
       kb0 = 0;
@@ -326,13 +330,16 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t buf_
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = false>
+// MODE: 0 = static deal of whole tiles (the shipped path), 1 = dynamic tile scheduler, 2 = tail split (static deal)
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = false, int MODE = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
             const __grid_constant__ CUtensorMap tmap_ws, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG, EPI, DEEP>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr bool DYN = MODE == 1;
+  constexpr bool TAIL = MODE == 2;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -399,9 +406,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // prologue done; operands / outputs of the predecessor kernel are touched only from here on
 
-  const int total_work = p.tail_splits > 1 ? p.full_tiles + (p.m_tiles * p.n_tiles - p.full_tiles) * p.tail_splits
-                                           : p.m_tiles * p.n_tiles * p.splits;
-  const TileSched sched{smem_u32(sched_ring), worker, n_workers, total_work, p.tile_counter};
+  const int total_work = TAIL ? p.full_tiles + (p.m_tiles * p.n_tiles - p.full_tiles) * p.tail_splits
+                              : p.m_tiles * p.n_tiles * p.splits;
+  const TileSched<DYN> sched{smem_u32(sched_ring), worker, n_workers, total_work, p.tile_counter};
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -417,7 +424,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int w = sched.get(seq);
         if (w >= total_work) break;
         int m_tile, n_tile, kb0, kb1, tail;
-        decode_work(p, w, m_tile, n_tile, kb0, kb1, tail);
+        decode_work<TAIL>(p, w, m_tile, n_tile, kb0, kb1, tail);
         if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;      // this CTA's 128 rows of the pair's 256
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -485,7 +492,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int w = sched.get(seq);
         if (w >= total_work) break;
         int m_tile, n_tile, kb0, kb1, tail;
-        decode_work(p, w, m_tile, n_tile, kb0, kb1, tail);
+        decode_work<TAIL>(p, w, m_tile, n_tile, kb0, kb1, tail);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -543,7 +550,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int w = sched.get(seq);
       if (w >= total_work) break;
       int m_tile, n_tile, kb0, kb1, tail;
-      decode_work(p, w, m_tile, n_tile, kb0, kb1, tail);
+      decode_work<TAIL>(p, w, m_tile, n_tile, kb0, kb1, tail);
       if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
       int turn = kb0 % p.n_tiles;       // k-block kb belongs to the item with n_tile == kb % n_tiles
       // lane -> (row phase rq = lane / 8, 16-byte piece c16 = lane % 8): one LDS.128 covers four token rows of the
@@ -643,7 +650,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int w = sched.get(wseq);
         if (w >= total_work) return;
         int m_t, n_t, k0_, k1_, tl_;
-        decode_work(p, w, m_t, n_t, k0_, k1_, tl_);
+        decode_work<TAIL>(p, w, m_t, n_t, k0_, k1_, tl_);
         if (CG == 2) m_t = m_t * 2 + (int)cta_rank;
         const int slot = (int)(seq % NAUX);
         mbar_expect_tx(&aux_full_bar[2 * grp + slot], EPI_BUF_BYTES);
@@ -657,7 +664,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int w = sched.get(wseq);
         if (w >= total_work) break;
         int m_tile, n_tile, kb0_, kb1_, tail;
-        decode_work(p, w, m_tile, n_tile, kb0_, kb1_, tail);
+        decode_work<TAIL>(p, w, m_tile, n_tile, kb0_, kb1_, tail);
         if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
         if (p.bias != nullptr) {
           if (et < BN / 2) {
@@ -678,7 +685,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // summed tile read back from the workspace (L2) instead of tensor memory, and leaves workspace and counter
         // zeroed for the next launch. Nobody waits for anybody.
         const float* ws_row = nullptr;     // non-null: this thread's row of the summed tile (last arriver of a split tile)
-        if (tail >= 0) {
+        if (TAIL && tail >= 0) {
           const int ws_r0 = (tail * CG + (int)cta_rank) * BM;      // first workspace row of this CTA's 128 tile rows
           float* ws_mine = p.tail_ws + (long long)(ws_r0 + row_in_tile) * BN;
           // (the same columns this group owns in the epilogue proper: rounds of CW columns, 32 at a time, staged in the
@@ -740,7 +747,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll 1      // (rolled: the unrolled round was 670 instructions, and 6 % of the epilogue's samples were i-cache misses)
           for (int hf = 0; hf < HALVES; ++hf) {
             uint32_t r[32];
-            if (ws_row != nullptr) {
+            if (TAIL && ws_row != nullptr) {
               // summed tile of a split tail tile: 128 contiguous bytes of this thread's workspace row, zeroed behind the read
               float4* src = reinterpret_cast<float4*>(const_cast<float*>(ws_row) + cc + 32 * hf);
 #pragma unroll
@@ -766,7 +773,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               // per thread sit in the memory pipe in front of these shared-memory reads, the barrier arrive overtakes them,
               // and the refill lands in rows that have not been read yet (seen on the GPU: the last two pieces of some
               // rows came from the NEXT round's columns). That route releases after the arithmetic has consumed ax[].
-              if (hf == HALVES - 1 && ws_row == nullptr) {
+              if (hf == HALVES - 1 && !(TAIL && ws_row != nullptr)) {
                 mbar_arrive(&aux_free_bar[2 * grp + aslot]);
                 if (et == 0) {
                   // refill this aux tile for the round NAUX rounds ahead (possibly of a later tile) once all have read it
@@ -777,7 +784,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               }
             }
             tmem_ld_wait();
-            if (ws_row == nullptr && rd == ROUNDS - 1 && hf == HALVES - 1) {   // last TMEM read of this accumulator stage: hand it back
+            if (!(TAIL && ws_row != nullptr) && rd == ROUNDS - 1 && hf == HALVES - 1) {   // last TMEM read of this accumulator stage: hand it back
               tc_fence_before();
               if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
               else mbar_arrive(&tmem_empty_bar[acc]);
@@ -847,7 +854,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 o[OUT_F32 ? 4 * q + 3 : 0] = __float_as_uint(v3);
               }
             }
-            if (AUX && hf == HALVES - 1 && ws_row != nullptr) {      // (see above: ax[] is in registers and consumed by now)
+            if (TAIL && AUX && hf == HALVES - 1 && ws_row != nullptr) {      // (see above: ax[] is in registers and consumed by now)
               mbar_arrive(&aux_free_bar[2 * grp + aslot]);
               if (et == 0) {
                 mbar_wait(&aux_free_bar[2 * grp + aslot], aphase);
@@ -888,7 +895,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int w = sched.get(wseq);
       if (w >= total_work) break;
       int m_tile, n_tile, kb0_, kb1_, tail_;
-      decode_work(p, w, m_tile, n_tile, kb0_, kb1_, tail_);
+      decode_work<TAIL>(p, w, m_tile, n_tile, kb0_, kb1_, tail_);
       if (CG == 2) m_tile = m_tile * 2 + (int)cta_rank;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -960,10 +967,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = false>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP, int MODE>
 static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tws,
                           const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG, DROP, DEEP>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CG, DROP, DEEP, MODE>;
   constexpr int SMEM = GemmCfg<BN, CG, EPI, DEEP>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
@@ -977,6 +984,20 @@ static int launch_gemm_cg(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   return 0;
 }
 
+// kernel variant by scheduling mode (the opt-in modes are separate instantiations, see TileSched)
+template <int BN, bool A_MN, bool B_MN, int EPI, int CG, bool DROP, bool DEEP = false>
+static int launch_gemm_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                            const CUtensorMap& tws, const GemmParams& p, int grid, cudaStream_t stream) {
+  if (p.tail_splits > 1) {
+    if constexpr (EPI == B200_EPI_STORE_BF16 || EPI == B200_EPI_RESID_F32)
+      return launch_gemm_cg<BN, A_MN, B_MN, EPI, CG, DROP, DEEP, 2>(ta, tb, to, to2, tws, p, grid, stream);
+    set_last_error("b200_gemm_bf16: tail split requested for an epilogue without it");
+    return -1;
+  }
+  if (p.tile_counter != nullptr) return launch_gemm_cg<BN, A_MN, B_MN, EPI, CG, DROP, DEEP, 1>(ta, tb, to, to2, tws, p, grid, stream);
+  return launch_gemm_cg<BN, A_MN, B_MN, EPI, CG, DROP, DEEP, 0>(ta, tb, to, to2, tws, p, grid, stream);
+}
+
 // p.m_tiles counts 256-row pair tiles when cta_pairs is set (BN = 256 only)
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const CUtensorMap& tws,
@@ -987,15 +1008,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const bool deep = HAS_DEEP && p.K >= 2048;
   if (CAN_DROP && p.drop_threshold16 != 0u) {
     if (BN == 256 && cta_pairs) {
-      if (deep) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP, HAS_DEEP>(ta, tb, to, to2, tws, p, grid, stream);
-      return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, CAN_DROP>(ta, tb, to, to2, tws, p, grid, stream);
+      if (deep) return launch_gemm_mode<256, A_MN, B_MN, EPI, 2, CAN_DROP, HAS_DEEP>(ta, tb, to, to2, tws, p, grid, stream);
+      return launch_gemm_mode<256, A_MN, B_MN, EPI, 2, CAN_DROP>(ta, tb, to, to2, tws, p, grid, stream);
     }
-    return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, CAN_DROP>(ta, tb, to, to2, tws, p, grid, stream);
+    return launch_gemm_mode<BN, A_MN, B_MN, EPI, 1, CAN_DROP>(ta, tb, to, to2, tws, p, grid, stream);
   }
   if (BN == 256 && cta_pairs && deep)
-    return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false, HAS_DEEP>(ta, tb, to, to2, tws, p, grid, stream);
-  if (BN == 256 && cta_pairs) return launch_gemm_cg<256, A_MN, B_MN, EPI, 2, false>(ta, tb, to, to2, tws, p, grid, stream);
-  return launch_gemm_cg<BN, A_MN, B_MN, EPI, 1, false>(ta, tb, to, to2, tws, p, grid, stream);
+    return launch_gemm_mode<256, A_MN, B_MN, EPI, 2, false, HAS_DEEP>(ta, tb, to, to2, tws, p, grid, stream);
+  if (BN == 256 && cta_pairs) return launch_gemm_mode<256, A_MN, B_MN, EPI, 2, false>(ta, tb, to, to2, tws, p, grid, stream);
+  return launch_gemm_mode<BN, A_MN, B_MN, EPI, 1, false>(ta, tb, to, to2, tws, p, grid, stream);
 }
 
 template <int BN, bool A_MN, bool B_MN>
